@@ -1,0 +1,398 @@
+// b2048_device.cuh -- device-side building blocks of the 2048 / n-tuple hot path (sm_100a).
+//
+// Everything here is a restatement, on packed 64-bit boards, of reference behaviour cited per
+// function as file:line under /root/reference (game2048/game_logic.py, game2048/r_learning.py).
+// Packed board: cell (r,c) = nibble at bit 4*(15-4r-c); row r = bits [63-16r : 48-16r].
+#pragma once
+#include <cstdint>
+#include <type_traits>
+#include <cuda_runtime.h>
+
+namespace b2048 {
+
+// portable intrinsics: the same functions compile for the host in tests/host_shim.cu, which lets the
+// CPU-only test tier check this header against the oracle without a GPU
+__host__ __device__ __forceinline__ int popc64(uint64_t x)
+{
+#ifdef __CUDA_ARCH__
+    return __popcll(x);
+#else
+    return __builtin_popcountll(x);
+#endif
+}
+
+__host__ __device__ __forceinline__ uint32_t umulhi32(uint32_t a, uint32_t b)
+{
+#ifdef __CUDA_ARCH__
+    return __umulhi(a, b);
+#else
+    return uint32_t((uint64_t(a) * b) >> 32);
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------
+// LUT entry (b2048_lut_build): bits 0-15 new line, 16-19 / 20-23 merge exponents, 24 changed, 25 overflow
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t LUT_CHANGED = 1u << 24;
+constexpr uint32_t LUT_OVERFLOW = 1u << 25;
+
+__host__ __device__ __forceinline__ uint32_t lut_score(uint32_t e)
+{
+    // score += 1 << (x + 1) per merge of two x tiles (game_logic.py:33)
+    uint32_t a = (e >> 16) & 15u, b = (e >> 20) & 15u;
+    return (a ? (2u << a) : 0u) + (b ? (2u << b) : 0u);
+}
+
+// create_table, game_logic.py:18-39, for one line (a,b,c,d) = nibbles 3..0 of `line`.
+__host__ __device__ inline uint32_t lut_entry(uint32_t line)
+{
+    int v[4] = {int(line >> 12) & 15, int(line >> 8) & 15, int(line >> 4) & 15, int(line) & 15};
+    int l1[4] = {0, 0, 0, 0}, n1 = 0;
+    for (int i = 0; i < 4; i++)
+        if (v[i]) l1[n1++] = v[i];                      // :29 drop zeros
+    uint32_t code = 0, nm = 0, ovf = 0;
+    for (int i = 0; i + 1 < n1; i++) {                  // :30-34 one left-to-right pass
+        int x = l1[i];
+        if (x && x == l1[i + 1]) {
+            code |= uint32_t(x) << (16 + 4 * nm++);
+            l1[i] = x + 1;
+            l1[i + 1] = 0;
+        }
+    }
+    uint32_t out = 0;
+    int n2 = 0;
+    for (int i = 0; i < n1; i++)                        // :35-36 drop zeros again, right-pad
+        if (l1[i]) {
+            int x = l1[i];
+            if (x > 15) { x = 15; ovf = 1; }            // 2^16 escape: saturate + flag
+            out |= uint32_t(x) << (12 - 4 * n2++);
+        }
+    uint32_t e = out | code;
+    // :37 changed = line != line_2 (on the unsaturated line: an overflowing line always changed)
+    if (out != line || ovf) e |= LUT_CHANGED;
+    if (ovf) e |= LUT_OVERFLOW;
+    return e;
+}
+
+// ------------------------------------------------------------------------------------------------
+// board symmetries (np.transpose / np.rot90 views of r_learning.py:207-214, game_logic.py:138-141)
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint64_t transpose(uint64_t x)
+{
+    uint64_t a1 = x & 0xF0F00F0FF0F00F0FULL;
+    uint64_t a2 = x & 0x0000F0F00000F0F0ULL;
+    uint64_t a3 = x & 0x0F0F00000F0F0000ULL;
+    uint64_t a = a1 | (a2 << 12) | (a3 >> 12);
+    uint64_t b1 = a & 0xFF00FF0000FF00FFULL;
+    uint64_t b2 = a & 0x00FF00FF00000000ULL;
+    uint64_t b3 = a & 0x00000000FF00FF00ULL;
+    return b1 | (b2 >> 24) | (b3 << 24);
+}
+
+// mirror the columns (reverse every row)
+__host__ __device__ __forceinline__ uint64_t flip_h(uint64_t x)
+{
+    return ((x & 0xF000F000F000F000ULL) >> 12) | ((x & 0x0F000F000F000F00ULL) >> 4) |
+           ((x & 0x00F000F000F000F0ULL) << 4) | ((x & 0x000F000F000F000FULL) << 12);
+}
+
+// mirror the rows (reverse the row order)
+__host__ __device__ __forceinline__ uint64_t flip_v(uint64_t x)
+{
+    return (x >> 48) | ((x >> 16) & 0x00000000FFFF0000ULL) | ((x << 16) & 0x0000FFFF00000000ULL) | (x << 48);
+}
+
+__host__ __device__ __forceinline__ uint32_t reverse_line(uint32_t r)
+{
+    return ((r & 0xF000u) >> 12) | ((r & 0x0F00u) >> 4) | ((r & 0x00F0u) << 4) | ((r & 0x000Fu) << 12);
+}
+
+// The 8 D4 images QAgent.update visits (r_learning.py:207-214: r, r^T, Rr, (Rr)^T, ... R = rot90).
+// As a set this is {id, flip_h, flip_v, flip_h.flip_v} x {id, transpose}; the order is irrelevant
+// because all 8 receive the same dw.  s in 0..7.
+__host__ __device__ __forceinline__ uint64_t d4_image(uint64_t b, int s)
+{
+    if (s & 1) b = flip_h(b);
+    if (s & 2) b = flip_v(b);
+    if (s & 4) b = transpose(b);
+    return b;
+}
+
+// ------------------------------------------------------------------------------------------------
+// board predicates (game_logic.py:96-110)
+// ------------------------------------------------------------------------------------------------
+// one bit per nibble (bit 4k set iff nibble k is zero)
+__host__ __device__ __forceinline__ uint64_t zero_nibbles(uint64_t x)
+{
+    uint64_t t = x | (x >> 1);
+    t |= t >> 2;
+    return ~t & 0x1111111111111111ULL;
+}
+
+__host__ __device__ __forceinline__ int empty_count(uint64_t b) { return popc64(zero_nibbles(b)); }   // :101-103
+
+// number of equal adjacent pairs (zeros included, like the reference's difference count), :105-107
+__host__ __device__ __forceinline__ int adjacent_pair_count(uint64_t b)
+{
+    uint64_t h = b ^ (b << 4);                       // nibble k vs nibble k-1 (same row if k%4 != 0)
+    uint64_t hz = zero_nibbles(h) & 0x1110111011101110ULL;
+    uint64_t v = b ^ (b << 16);                      // row r vs row r+1
+    uint64_t vz = zero_nibbles(v) & 0x1111111111110000ULL;
+    return popc64(hz) + popc64(vz);
+}
+
+__host__ __device__ __forceinline__ bool game_over(uint64_t b)                                           // :109-110
+{
+    return zero_nibbles(b) == 0 && adjacent_pair_count(b) == 0;
+}
+
+__host__ __device__ __forceinline__ int max_tile(uint64_t b)
+{
+    int best = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        int v = int((b >> (4 * k)) & 15);
+        best = v > best ? v : best;
+    }
+    return best;
+}
+
+// ------------------------------------------------------------------------------------------------
+// moves: Game._left / pre_move (game_logic.py:123-142).  LutT provides operator()(line) -> entry
+// ------------------------------------------------------------------------------------------------
+struct LutGlobal {
+    const uint32_t *__restrict__ p;
+    __device__ __forceinline__ uint32_t operator()(uint32_t line) const { return __ldg(p + line); }
+};
+
+// slide+merge every row to the left.  ok bits: 1 changed, 2 overflow
+template <class LutT>
+__host__ __device__ __forceinline__ uint64_t move_left(const LutT &lut, uint64_t b, uint32_t &gain, uint32_t &flags)
+{
+    uint64_t out = 0;
+    uint32_t fl = 0, g = 0;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        uint32_t e = lut(uint32_t(b >> (48 - 16 * r)) & 0xFFFFu);
+        out |= uint64_t(e & 0xFFFFu) << (48 - 16 * r);
+        g += lut_score(e);
+        fl |= e >> 24;
+    }
+    gain = g;
+    flags = fl & 3u;
+    return out;
+}
+
+template <class LutT>
+__host__ __device__ __forceinline__ uint64_t move_right(const LutT &lut, uint64_t b, uint32_t &gain, uint32_t &flags)
+{
+    uint64_t out = 0;
+    uint32_t fl = 0, g = 0;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        uint32_t e = lut(reverse_line(uint32_t(b >> (48 - 16 * r)) & 0xFFFFu));
+        out |= uint64_t(reverse_line(e & 0xFFFFu)) << (48 - 16 * r);
+        g += lut_score(e);
+        fl |= e >> 24;
+    }
+    gain = g;
+    flags = fl & 3u;
+    return out;
+}
+
+// pre_move(row, score, d): d = 0 left, 1 up, 2 right, 3 down (game_logic.py:50,136-142):
+// rot90(row, d) -> left -> rot90 back  ==  up: transpose/left/transpose, right: mirror/left/mirror,
+// down: transpose/right/transpose.
+template <class LutT>
+__host__ __device__ __forceinline__ uint64_t move_dir(const LutT &lut, uint64_t b, int d, uint32_t &gain, uint32_t &flags)
+{
+    uint64_t x = (d & 1) ? transpose(b) : b;
+    uint64_t y = (d & 2) ? move_right(lut, x, gain, flags) : move_left(lut, x, gain, flags);
+    return (d & 1) ? transpose(y) : y;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11) and the spawn rule (game_logic.py:112-121 with Philox words)
+// ------------------------------------------------------------------------------------------------
+struct Philox4 {
+    uint32_t x, y, z, w;
+};
+
+__host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                          uint32_t k0, uint32_t k1)
+{
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint64_t p0 = uint64_t(0xD2511F53u) * c0;
+        uint64_t p1 = uint64_t(0xCD9E8D57u) * c2;
+        uint32_t n0 = uint32_t(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n2 = uint32_t(p0 >> 32) ^ c3 ^ k1;
+        c1 = uint32_t(p1);
+        c3 = uint32_t(p0);
+        c0 = n0;
+        c2 = n2;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return Philox4{c0, c1, c2, c3};
+}
+
+__host__ __device__ __forceinline__ Philox4 spawn_words(uint64_t seed, uint64_t id, uint32_t move_no, uint32_t purpose)
+{
+    return philox4x32_10(uint32_t(id), uint32_t(id >> 32), move_no, purpose, uint32_t(seed), uint32_t(seed >> 32));
+}
+
+// position (bit index, multiple of 4) of the k-th set bit of a one-bit-per-nibble mask, counting
+// nibbles in row-major order, i.e. from the MOST significant nibble.
+__host__ __device__ __forceinline__ int kth_empty_shift(uint64_t zmask, int k)
+{
+    // row-major order = descending bit position: skip the k highest set bits, take the next one
+    // (branch-free select over the 16 nibbles, no local arrays)
+    int sh = 0;
+#pragma unroll
+    for (int q = 15; q >= 0; q--) {
+        int bit = int((zmask >> (4 * q)) & 1u);
+        if (bit && k == 0) sh = 4 * q;
+        k -= bit;
+    }
+    return sh;
+}
+
+// create_new_tile: tile = 2 iff floor(10 u0) == 0, cell = floor(n_empty u1)-th empty cell, row-major.
+// Returns (tile << 8) | flat cell, or 0xFFFF if the board is full.
+__host__ __device__ __forceinline__ uint32_t spawn_apply(uint64_t &b, uint32_t r_tile, uint32_t r_pos)
+{
+    uint64_t z = zero_nibbles(b);
+    int m = popc64(z);
+    if (m == 0) return 0xFFFFu;
+    uint32_t tile = umulhi32(r_tile, 10u) == 0 ? 2u : 1u;
+    int k = int(umulhi32(r_pos, uint32_t(m)));
+    int sh = kth_empty_shift(z, k);
+    b |= uint64_t(tile) << sh;
+    return (tile << 8) | uint32_t(15 - sh / 4);
+}
+
+// Game.__init__ (game_logic.py:61-66): two spawns on the empty board
+__host__ __device__ __forceinline__ uint64_t spawn_initial(uint64_t seed, uint64_t id)
+{
+    Philox4 w = spawn_words(seed, id, 0u, 0u);
+    uint64_t b = 0;
+    spawn_apply(b, w.x, w.y);
+    spawn_apply(b, w.z, w.w);
+    return b;
+}
+
+// ------------------------------------------------------------------------------------------------
+// n-tuple features (r_learning.py:17-69), compile-time cell lists
+// ------------------------------------------------------------------------------------------------
+struct FeatSpec {
+    int ncell;      // cells per tuple
+    int cell[6];    // flat positions 4r+c, most significant first
+    int base;       // 16 (shift/or) or 14 (n=6 extra tuples on y = min(x, 13))
+};
+
+__host__ __device__ constexpr int num_feat(int n) { return n == 2 ? 24 : n == 3 ? 52 : n == 4 ? 17 : n == 5 ? 21 : n == 6 ? 33 : -1; }
+
+__host__ __device__ constexpr int P(int r, int c) { return 4 * r + c; }
+
+__host__ __device__ constexpr FeatSpec feat_spec(int n, int i)
+{
+    if (n == 2) {                                    // f_2 :17-20
+        if (i < 12) return FeatSpec{2, {P(i / 4, i % 4), P(i / 4 + 1, i % 4), 0, 0, 0, 0}, 16};
+        int k = i - 12;
+        return FeatSpec{2, {P(k / 3, k % 3), P(k / 3, k % 3 + 1), 0, 0, 0, 0}, 16};
+    }
+    if (n == 3) {                                    // f_3 :24-31
+        if (i < 8) return FeatSpec{3, {P(i / 4, i % 4), P(i / 4 + 1, i % 4), P(i / 4 + 2, i % 4), 0, 0, 0}, 16};
+        if (i < 16) {
+            int k = i - 8;
+            return FeatSpec{3, {P(k / 2, k % 2), P(k / 2, k % 2 + 1), P(k / 2, k % 2 + 2), 0, 0, 0}, 16};
+        }
+        int k = i - 16, g = k / 9, r = (k % 9) / 3, c = k % 3;
+        if (g == 0) return FeatSpec{3, {P(r + 1, c), P(r + 1, c + 1), P(r, c + 1), 0, 0, 0}, 16};   // ex_00
+        if (g == 1) return FeatSpec{3, {P(r, c), P(r + 1, c), P(r + 1, c + 1), 0, 0, 0}, 16};       // ex_01
+        if (g == 2) return FeatSpec{3, {P(r, c), P(r, c + 1), P(r + 1, c + 1), 0, 0, 0}, 16};       // ex_10
+        return FeatSpec{3, {P(r, c), P(r + 1, c), P(r, c + 1), 0, 0, 0}, 16};                       // ex_11
+    }
+    // f_4 :40-44 is the prefix of f_5 :48-54 and f_6 :58-69
+    if (i < 4) return FeatSpec{4, {P(0, i), P(1, i), P(2, i), P(3, i), 0, 0}, 16};                  // columns
+    if (i < 8) return FeatSpec{4, {P(i - 4, 0), P(i - 4, 1), P(i - 4, 2), P(i - 4, 3), 0, 0}, 16};  // rows
+    if (i < 17) {
+        int r = (i - 8) / 3, c = (i - 8) % 3;                                                       // squares
+        return FeatSpec{4, {P(r, c), P(r + 1, c), P(r, c + 1), P(r + 1, c + 1), 0, 0}, 16};
+    }
+    if (i < 21) {
+        int a = 1 + (i - 17) / 2, b = 1 + (i - 17) % 2;                                             // crosses
+        return FeatSpec{5, {P(a, b), P(a - 1, b), P(a, b - 1), P(a + 1, b), P(a, b + 1), 0}, 16};
+    }
+    if (i < 27) {
+        int r = (i - 21) / 3, c = (i - 21) % 3;                                                     // 3x2 rects
+        return FeatSpec{6, {P(r, c), P(r + 1, c), P(r + 2, c), P(r, c + 1), P(r + 1, c + 1), P(r + 2, c + 1)}, 14};
+    }
+    int r = (i - 27) / 2, c = (i - 27) % 2;                                                         // 2x3 rects
+    return FeatSpec{6, {P(r, c), P(r, c + 1), P(r, c + 2), P(r + 1, c), P(r + 1, c + 1), P(r + 1, c + 2)}, 14};
+}
+
+__host__ __device__ constexpr int64_t table_size(int n, int i)
+{
+    return n == 2 ? 256 : n == 3 ? 4096 : i < 17 ? 65536 : i < 21 ? 1048576 : 7529536;   // r_learning.py:88,136-149
+}
+
+__host__ __device__ constexpr int64_t table_offset(int n, int i)
+{
+    int64_t o = 0;
+    for (int k = 0; k < i; k++) o += table_size(n, k);
+    return o;
+}
+
+// y = min(x, 13) on all 16 nibbles at once (r_learning.py:64)
+__host__ __device__ __forceinline__ uint64_t clamp13(uint64_t x)
+{
+    uint64_t t = (x >> 3) & (x >> 2) & (x >> 1) & 0x1111111111111111ULL;   // nibble >= 14
+    return (x & ~(t << 1)) | t;                                               // 111x -> 1101
+}
+
+template <int N, int I>
+__host__ __device__ __forceinline__ uint32_t feat_index(uint64_t b, uint64_t y)
+{
+    constexpr FeatSpec s = feat_spec(N, I);
+    uint32_t idx = 0;
+    if constexpr (s.base == 16) {
+#pragma unroll
+        for (int k = 0; k < s.ncell; k++)
+            idx |= (uint32_t(b >> (4 * (15 - s.cell[k]))) & 15u) << (4 * (s.ncell - 1 - k));
+    } else {
+#pragma unroll
+        for (int k = 0; k < s.ncell; k++) idx = idx * 14u + (uint32_t(y >> (4 * (15 - s.cell[k]))) & 15u);
+    }
+    return idx;
+}
+
+// calls f(std::integral_constant<int, I>) for I = 0..F-1 (compile-time unrolled)
+template <int N, int I = 0, class Fn>
+__host__ __device__ __forceinline__ void for_each_feature(Fn &&f)
+{
+    if constexpr (I < num_feat(N)) {
+        f(std::integral_constant<int, I>{});
+        for_each_feature<N, I + 1>(f);
+    }
+}
+
+// QAgent.evaluate (r_learning.py:202-203): sequential float32 sum in table order, from 0.
+template <int N>
+__device__ __forceinline__ float evaluate(const float *__restrict__ w, uint64_t b)
+{
+    constexpr int F = num_feat(N);
+    const uint64_t y = (N == 6) ? clamp13(b) : 0;
+    float v[F];
+    for_each_feature<N>([&](auto I) {
+        constexpr int i = decltype(I)::value;
+        v[i] = __ldg(w + table_offset(N, i) + feat_index<N, i>(b, y));   // all gathers in flight first
+    });
+    float acc = 0.0f;
+#pragma unroll
+    for (int i = 0; i < F; i++) acc = __fadd_rn(acc, v[i]);
+    return acc;
+}
+
+}   // namespace b2048

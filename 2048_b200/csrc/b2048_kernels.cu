@@ -1,0 +1,1102 @@
+// b2048_kernels.cu -- CUDA kernels (sm_100a) + the C-ABI of include/b2048.h.
+//
+// Kernel groups (BASELINE.json north_star): (1) packed boards, (2) LUT moves, (3) Philox / replay
+// spawns, (4) n-tuple gather (evaluate) and TD scatter (atomic | deterministic, sum | per-key mean),
+// plus the fused game loops built from the same device functions (b2048_device.cuh).
+// Nothing here is a dense contraction: no tensor cores by design (HBM/L2-latency- and issue-bound).
+#include <cstdint>
+#include <cstdio>
+#include <cmath>
+#include <type_traits>
+
+#include <cuda_runtime.h>
+
+#include "b2048_device.cuh"
+#include "../../include/b2048.h"
+
+using namespace b2048;
+
+namespace {
+
+constexpr unsigned FULL = 0xFFFFFFFFu;
+
+inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+inline int launch_status()
+{
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : int(e);
+}
+
+inline cudaStream_t S(b2048_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// number of SMs of the current device (cached per device id; immutable)
+int sm_count()
+{
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (!cached[dev]) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+// ------------------------------------------------------------------------------------------------
+// (1) pack / unpack
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_kernel(const int32_t *__restrict__ rows, uint64_t *__restrict__ boards, int64_t m)
+{
+    int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (i >= m) return;
+    const int4 *r = reinterpret_cast<const int4 *>(rows + 16 * i);
+    uint64_t b = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        int4 v = __ldg(r + q);
+        uint64_t line = (uint64_t(v.x & 15) << 12) | (uint64_t(v.y & 15) << 8) | (uint64_t(v.z & 15) << 4) | uint64_t(v.w & 15);
+        b |= line << (48 - 16 * q);
+    }
+    boards[i] = b;
+}
+
+__global__ void unpack_kernel(const uint64_t *__restrict__ boards, int32_t *__restrict__ rows, int64_t m)
+{
+    int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (i >= m) return;
+    uint64_t b = __ldg(boards + i);
+    int4 *r = reinterpret_cast<int4 *>(rows + 16 * i);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        uint32_t line = uint32_t(b >> (48 - 16 * q)) & 0xFFFFu;
+        r[q] = make_int4(int(line >> 12) & 15, int(line >> 8) & 15, int(line >> 4) & 15, int(line) & 15);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// (2) moves
+// ------------------------------------------------------------------------------------------------
+__global__ void lut_build_kernel(uint32_t *__restrict__ lut)
+{
+    uint32_t line = blockIdx.x * blockDim.x + threadIdx.x;
+    if (line < B2048_LUT_ENTRIES) lut[line] = lut_entry(line);
+}
+
+__global__ void move4_kernel(const uint32_t *__restrict__ lut, const uint64_t *__restrict__ boards, int64_t m,
+                             uint64_t *__restrict__ after, uint32_t *__restrict__ gain, uint8_t *__restrict__ flags,
+                             uint8_t *__restrict__ over)
+{
+    int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (i >= m) return;
+    LutGlobal L{lut};
+    uint64_t b = __ldg(boards + i);
+    uint64_t a[4];
+    uint32_t g[4], fl = 0;
+#pragma unroll
+    for (int d = 0; d < 4; d++) {
+        uint32_t f;
+        a[d] = move_dir(L, b, d, g[d], f);
+        fl |= (f & 1u) << d;
+        fl |= ((f >> 1) & 1u) << (4 + d);
+    }
+    ulonglong2 *ap = reinterpret_cast<ulonglong2 *>(after + 4 * i);
+    ap[0] = make_ulonglong2(a[0], a[1]);
+    ap[1] = make_ulonglong2(a[2], a[3]);
+    *reinterpret_cast<uint4 *>(gain + 4 * i) = make_uint4(g[0], g[1], g[2], g[3]);
+    flags[i] = uint8_t(fl);
+    if (over) over[i] = game_over(b) ? 1 : 0;
+}
+
+__global__ void board_stats_kernel(const uint64_t *__restrict__ boards, int64_t m, uint8_t *__restrict__ stats,
+                                   uint16_t *__restrict__ empty_mask)
+{
+    int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (i >= m) return;
+    uint64_t b = __ldg(boards + i);
+    uint64_t z = zero_nibbles(b);
+    int ne = __popcll(z), np = adjacent_pair_count(b);
+    if (stats) {
+        uchar4 s = make_uchar4((unsigned char)ne, (unsigned char)np, (unsigned char)(ne == 0 && np == 0),
+                               (unsigned char)max_tile(b));
+        reinterpret_cast<uchar4 *>(stats)[i] = s;
+    }
+    if (empty_mask) {
+        uint32_t mask = 0;
+#pragma unroll
+        for (int p = 0; p < 16; p++) mask |= uint32_t((z >> (4 * (15 - p))) & 1u) << p;
+        empty_mask[i] = uint16_t(mask);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// (3) spawns
+// ------------------------------------------------------------------------------------------------
+__global__ void spawn_philox_kernel(uint64_t *__restrict__ boards, int64_t m, uint64_t seed,
+                                    const uint64_t *__restrict__ game_id, const uint32_t *__restrict__ move_no,
+                                    uint16_t *__restrict__ spawn)
+{
+    int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (i >= m) return;
+    uint64_t b = boards[i];
+    Philox4 w = spawn_words(seed, __ldg(game_id + i), __ldg(move_no + i), 0u);
+    uint32_t res = spawn_apply(b, w.x, w.y);
+    boards[i] = b;
+    if (spawn) spawn[i] = uint16_t(res);
+}
+
+__global__ void spawn_initial_kernel(uint64_t *__restrict__ boards, int64_t m, uint64_t seed, uint64_t first_id,
+                                     uint64_t id_step)
+{
+    int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (i >= m) return;
+    boards[i] = spawn_initial(seed, first_id + uint64_t(i) * id_step);
+}
+
+__global__ void spawn_replay_kernel(uint64_t *__restrict__ boards, int64_t m, const uint8_t *__restrict__ tile,
+                                    const uint8_t *__restrict__ pos)
+{
+    int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (i >= m) return;
+    uint32_t t = tile[i];
+    if (!t) return;
+    int sh = 4 * (15 - int(pos[i] & 15));
+    uint64_t b = boards[i];
+    boards[i] = (b & ~(0xFULL << sh)) | (uint64_t(t & 15u) << sh);     // row[pos] = tile (game_logic.py:260)
+}
+
+// config-5 sweep: persistent CTAs, row LUT (u16) + merge-code LUT (u8) staged in 192 KB of shared memory
+struct LutShared {
+    const uint16_t *row;
+    const uint8_t *code;
+    __device__ __forceinline__ uint32_t operator()(uint32_t line) const
+    {
+        uint32_t r = row[line], c = code[line];
+        uint32_t ovf = ((c & 15u) == 15u) | ((c >> 4) == 15u);
+        uint32_t ch = (r != line) | ovf;
+        return r | (c << 16) | (ch << 24) | (ovf << 25);
+    }
+};
+
+constexpr int SWEEP_THREADS = 1024;
+constexpr size_t SWEEP_SMEM = 65536 * 2 + 65536;
+
+__global__ void __launch_bounds__(SWEEP_THREADS, 1)
+sweep_kernel(const uint32_t *__restrict__ lut, const uint64_t *__restrict__ boards, int64_t m, uint64_t seed,
+             uint64_t first_index, uint64_t *__restrict__ after, uint32_t *__restrict__ gain,
+             uint8_t *__restrict__ flags, uint64_t *__restrict__ spawned)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    uint16_t *srow = reinterpret_cast<uint16_t *>(smem);
+    uint8_t *scode = smem + 65536 * 2;
+    // stage: 4 entries per thread per iteration (16 B global load -> 8 B + 4 B shared stores)
+    for (int q = threadIdx.x; q < 65536 / 4; q += SWEEP_THREADS) {
+        uint4 e = __ldg(reinterpret_cast<const uint4 *>(lut) + q);
+        uint2 r = make_uint2((e.x & 0xFFFFu) | (e.y << 16), (e.z & 0xFFFFu) | (e.w << 16));
+        reinterpret_cast<uint2 *>(srow)[q] = r;
+        uint32_t c = ((e.x >> 16) & 0xFFu) | (((e.y >> 16) & 0xFFu) << 8) | (((e.z >> 16) & 0xFFu) << 16) |
+                     (((e.w >> 16) & 0xFFu) << 24);
+        reinterpret_cast<uint32_t *>(scode)[q] = c;
+    }
+    __syncthreads();
+    LutShared L{srow, scode};
+    const int64_t stride = int64_t(gridDim.x) * SWEEP_THREADS;
+    for (int64_t i = blockIdx.x * int64_t(SWEEP_THREADS) + threadIdx.x; i < m; i += stride) {
+        uint64_t b = __ldg(boards + i);
+        uint64_t a[4];
+        uint32_t g[4], fl = 0, ok = 0;
+#pragma unroll
+        for (int d = 0; d < 4; d++) {
+            uint32_t f;
+            a[d] = move_dir(L, b, d, g[d], f);
+            fl |= (f & 1u) << d;
+            fl |= ((f >> 1) & 1u) << (4 + d);
+            ok |= uint32_t((f & 3u) == 1u) << d;
+        }
+        ulonglong2 *ap = reinterpret_cast<ulonglong2 *>(after + 4 * i);
+        ap[0] = make_ulonglong2(a[0], a[1]);
+        ap[1] = make_ulonglong2(a[2], a[3]);
+        *reinterpret_cast<uint4 *>(gain + 4 * i) = make_uint4(g[0], g[1], g[2], g[3]);
+        flags[i] = uint8_t(fl);
+        if (spawned) {
+            uint64_t idx = first_index + uint64_t(i);
+            if (ok & 3u) {
+                Philox4 w = spawn_words(seed, idx, 0u, 1u);
+                if (ok & 1u) spawn_apply(a[0], w.x, w.y);
+                if (ok & 2u) spawn_apply(a[1], w.z, w.w);
+            }
+            if (ok & 12u) {
+                Philox4 w = spawn_words(seed, idx, 1u, 1u);
+                if (ok & 4u) spawn_apply(a[2], w.x, w.y);
+                if (ok & 8u) spawn_apply(a[3], w.z, w.w);
+            }
+            ulonglong2 *sp = reinterpret_cast<ulonglong2 *>(spawned + 4 * i);
+            sp[0] = make_ulonglong2(a[0], a[1]);
+            sp[1] = make_ulonglong2(a[2], a[3]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// (4) features / evaluate
+// ------------------------------------------------------------------------------------------------
+template <int N>
+__global__ void features_kernel(const uint64_t *__restrict__ boards, int64_t m, int32_t *__restrict__ feat)
+{
+    int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (i >= m) return;
+    constexpr int F = num_feat(N);
+    uint64_t b = __ldg(boards + i);
+    uint64_t y = (N == 6) ? clamp13(b) : 0;
+    int32_t *o = feat + i * F;
+    for_each_feature<N>([&](auto I) {
+        constexpr int k = decltype(I)::value;
+        o[k] = int32_t(feat_index<N, k>(b, y));
+    });
+}
+
+template <int N>
+__global__ void evaluate_kernel(const float *__restrict__ w, const uint64_t *__restrict__ boards, int64_t m,
+                                float *__restrict__ value)
+{
+    int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (i >= m) return;
+    value[i] = evaluate<N>(w, __ldg(boards + i));
+}
+
+// ------------------------------------------------------------------------------------------------
+// TD update: 8 D4 images x F tables per (board, dw)
+// ------------------------------------------------------------------------------------------------
+// red.global.add.f32 (no return value -> fire and forget)
+__device__ __forceinline__ void red_add(float *p, float v) { atomicAdd(p, v); }
+
+// atomic, sum rule: thread per (entry j, image s)
+template <int N>
+__global__ void td_update_atomic_sum_kernel(float *__restrict__ w, float *__restrict__ delta,
+                                            const uint64_t *__restrict__ boards, const float *__restrict__ dw, int64_t m)
+{
+    int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    int64_t j = t >> 3;
+    if (j >= m) return;
+    float d = __ldg(dw + j);
+    if (isnan(d)) return;
+    uint64_t b = d4_image(__ldg(boards + j), int(t & 7));
+    uint64_t y = (N == 6) ? clamp13(b) : 0;
+    for_each_feature<N>([&](auto I) {
+        constexpr int i = decltype(I)::value;
+        int64_t k = table_offset(N, i) + feat_index<N, i>(b, y);
+        red_add(w + k, d);
+        if (delta) red_add(delta + k, d);
+    });
+}
+
+// atomic, per-key-mean rule, pass 1: acc[k] += dw per contribution, cnt[k] += 1 per DISTINCT entry
+// (a key can repeat among the 8 images of one board: only the first image holding it counts).
+// Thread per (entry, image); the 8 images of an entry are 8 adjacent lanes.
+template <int N>
+__global__ void td_update_mean_accum_kernel(float *__restrict__ acc, uint32_t *__restrict__ cnt,
+                                            const uint64_t *__restrict__ boards, const float *__restrict__ dw, int64_t m)
+{
+    int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    int64_t j = t >> 3;
+    const int s = int(t & 7);
+    const bool on = j < m;
+    float d = on ? __ldg(dw + j) : NAN;
+    const bool live = on && !isnan(d);
+    uint64_t b = d4_image(on ? __ldg(boards + j) : 0, s);
+    uint64_t y = (N == 6) ? clamp13(b) : 0;
+    for_each_feature<N>([&](auto I) {
+        constexpr int i = decltype(I)::value;
+        uint32_t f = feat_index<N, i>(b, y);
+        bool first = true;
+#pragma unroll
+        for (int o = 1; o < 8; o++) {                 // same table, other images of the same entry
+            uint32_t fo = __shfl_xor_sync(FULL, f, o);
+            if (fo == f && (s ^ o) < s) first = false;
+        }
+        if (live) {
+            int64_t k = table_offset(N, i) + f;
+            red_add(acc + k, d);
+            if (first) atomicAdd(cnt + k, 1u);
+        }
+    });
+}
+
+// pass 2: whoever swaps the count out applies  w[k] += acc[k] / cnt  and clears acc[k]
+template <int N>
+__global__ void td_update_mean_apply_kernel(float *__restrict__ w, float *__restrict__ delta, float *__restrict__ acc,
+                                            uint32_t *__restrict__ cnt, const uint64_t *__restrict__ boards,
+                                            const float *__restrict__ dw, int64_t m)
+{
+    int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    int64_t j = t >> 3;
+    if (j >= m) return;
+    float d = __ldg(dw + j);
+    if (isnan(d)) return;
+    uint64_t b = d4_image(__ldg(boards + j), int(t & 7));
+    uint64_t y = (N == 6) ? clamp13(b) : 0;
+    for_each_feature<N>([&](auto I) {
+        constexpr int i = decltype(I)::value;
+        int64_t k = table_offset(N, i) + feat_index<N, i>(b, y);
+        uint32_t c = atomicExch(cnt + k, 0u);
+        if (c) {
+            float u = __fdiv_rn(acc[k], float(c));
+            acc[k] = 0.0f;
+            w[k] = __fadd_rn(w[k], u);
+            if (delta) delta[k] = __fadd_rn(delta[k], u);
+        }
+    });
+}
+
+// deterministic: key generation -> stable LSD radix sort of (key, entry) -> per-key sequential sums
+template <int N>
+__global__ void td_keys_kernel(const uint64_t *__restrict__ boards, const float *__restrict__ dw, int64_t m,
+                               uint32_t *__restrict__ keys, uint32_t *__restrict__ vals)
+{
+    int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    int64_t j = t >> 3;
+    if (j >= m) return;
+    constexpr int F = num_feat(N);
+    const int s = int(t & 7);
+    float d = __ldg(dw + j);
+    const bool live = !isnan(d);
+    uint64_t b = d4_image(__ldg(boards + j), s);
+    uint64_t y = (N == 6) ? clamp13(b) : 0;
+    uint32_t *ko = keys + (j * 8 + s) * F;
+    uint32_t *vo = vals + (j * 8 + s) * F;
+    for_each_feature<N>([&](auto I) {
+        constexpr int i = decltype(I)::value;
+        ko[i] = live ? uint32_t(table_offset(N, i) + feat_index<N, i>(b, y)) : 0xFFFFFFFFu;
+        vo[i] = uint32_t(j);
+    });
+}
+
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_ITEMS = 8;
+constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
+constexpr int SORT_WARPS = SORT_THREADS / 32;
+
+template <int BITS>
+__global__ void __launch_bounds__(SORT_THREADS)
+radix_hist_kernel(const uint32_t *__restrict__ keys, int64_t M, int shift, uint32_t *__restrict__ hist, int nblocks)
+{
+    constexpr int RADIX = 1 << BITS;
+    __shared__ uint32_t h[RADIX];
+    for (int q = threadIdx.x; q < RADIX; q += SORT_THREADS) h[q] = 0;
+    __syncthreads();
+    int64_t base = int64_t(blockIdx.x) * SORT_TILE;
+#pragma unroll
+    for (int it = 0; it < SORT_ITEMS; it++) {
+        int64_t idx = base + it * SORT_THREADS + threadIdx.x;
+        if (idx < M) atomicAdd(&h[(__ldg(keys + idx) >> shift) & (RADIX - 1)], 1u);
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < RADIX; q += SORT_THREADS) hist[int64_t(q) * nblocks + blockIdx.x] = h[q];
+}
+
+// exclusive scan of `count` uint32 in place, one block
+__global__ void __launch_bounds__(1024) scan_kernel(uint32_t *__restrict__ data, int64_t count)
+{
+    __shared__ uint32_t part[1024];
+    const int t = threadIdx.x;
+    int64_t chunk = (count + 1023) / 1024;
+    int64_t lo = t * chunk, hi = lo + chunk < count ? lo + chunk : count;
+    uint32_t s = 0;
+    for (int64_t q = lo; q < hi; q++) s += data[q];
+    part[t] = s;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {       // Hillis-Steele inclusive scan
+        uint32_t v = t >= off ? part[t - off] : 0;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    uint32_t run = part[t] - s;
+    for (int64_t q = lo; q < hi; q++) {
+        uint32_t v = data[q];
+        data[q] = run;
+        run += v;
+    }
+}
+
+template <int BITS>
+__global__ void __launch_bounds__(SORT_THREADS)
+radix_scatter_kernel(const uint32_t *__restrict__ kin, const uint32_t *__restrict__ vin, uint32_t *__restrict__ kout,
+                     uint32_t *__restrict__ vout, const uint32_t *__restrict__ offs, int64_t M, int shift, int nblocks)
+{
+    constexpr int RADIX = 1 << BITS;
+    __shared__ uint32_t wcount[SORT_WARPS][RADIX];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int q = threadIdx.x; q < SORT_WARPS * RADIX; q += SORT_THREADS) (&wcount[0][0])[q] = 0;
+    __syncthreads();
+    // warp-striped tile: warp w owns 256 consecutive elements; item it covers 32 consecutive ones,
+    // so (it, lane) order == input order (needed for stability)
+    const int64_t wbase = int64_t(blockIdx.x) * SORT_TILE + warp * (32 * SORT_ITEMS);
+    uint32_t key[SORT_ITEMS], val[SORT_ITEMS], rank[SORT_ITEMS];
+#pragma unroll
+    for (int it = 0; it < SORT_ITEMS; it++) {
+        int64_t idx = wbase + it * 32 + lane;
+        bool valid = idx < M;
+        key[it] = valid ? __ldg(kin + idx) : 0u;
+        val[it] = valid ? __ldg(vin + idx) : 0u;
+        uint32_t digit = valid ? ((key[it] >> shift) & (RADIX - 1)) : RADIX;      // RADIX = "no element"
+        uint32_t peers = __match_any_sync(FULL, digit);
+        int leader = __ffs(peers) - 1;
+        uint32_t old = 0;
+        if (valid && lane == leader) {
+            old = wcount[warp][digit];
+            wcount[warp][digit] = old + __popc(peers);
+        }
+        old = __shfl_sync(FULL, old, leader);
+        rank[it] = old + __popc(peers & ((1u << lane) - 1u));
+        __syncwarp();
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < RADIX; q += SORT_THREADS) {
+        uint32_t run = __ldg(offs + int64_t(q) * nblocks + blockIdx.x);
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; w++) {
+            uint32_t c = wcount[w][q];
+            wcount[w][q] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < SORT_ITEMS; it++) {
+        int64_t idx = wbase + it * 32 + lane;
+        if (idx < M) {
+            uint32_t pos = wcount[warp][(key[it] >> shift) & (RADIX - 1)] + rank[it];
+            kout[pos] = key[it];
+            vout[pos] = val[it];
+        }
+    }
+}
+
+// sorted (key, entry): the thread at the head of each key run sums its contributions in order
+__global__ void td_segment_apply_kernel(float *__restrict__ w, float *__restrict__ delta,
+                                        const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals,
+                                        const float *__restrict__ dw, int64_t M, int mean)
+{
+    int64_t p = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (p >= M) return;
+    uint32_t k = __ldg(keys + p);
+    if (k == 0xFFFFFFFFu) return;
+    if (p > 0 && __ldg(keys + p - 1) == k) return;
+    float s = 0.0f;
+    uint32_t g = 0, last = 0xFFFFFFFFu;
+    for (int64_t q = p; q < M && __ldg(keys + q) == k; q++) {
+        uint32_t j = __ldg(vals + q);
+        s = __fadd_rn(s, __ldg(dw + j));
+        g += (j != last);
+        last = j;
+    }
+    float u = mean ? __fdiv_rn(s, float(g)) : s;
+    w[k] = __fadd_rn(w[k], u);
+    if (delta) delta[k] = __fadd_rn(delta[k], u);
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused game loops
+// ------------------------------------------------------------------------------------------------
+__global__ void games_init_kernel(b2048_games_t g, uint64_t first_id, int reset_counters)
+{
+    int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if (reset_counters && i < B2048_CTR_COUNT) g.counters[i] = 0;
+    if (reset_counters && i < 17) g.tile_hist[i] = 0;
+    if (i >= g.B) return;
+    uint64_t id = first_id + uint64_t(i);
+    g.game_id[i] = id;
+    g.board[i] = spawn_initial(g.seed, id);
+    g.score[i] = 0;
+    g.moves[i] = 0;
+    g.state[i] = 0;
+    g.old_label[i] = 0.0f;
+    g.flags[i] = 0;
+}
+
+__device__ __forceinline__ uint64_t shfl64(uint64_t v, int src, int width)
+{
+    uint32_t lo = __shfl_sync(FULL, uint32_t(v), src, width);
+    uint32_t hi = __shfl_sync(FULL, uint32_t(v >> 32), src, width);
+    return (uint64_t(hi) << 32) | lo;
+}
+
+__device__ __forceinline__ void warp_add_counter(uint64_t *ctr, uint32_t v)
+{
+    v = __reduce_add_sync(FULL, v);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(reinterpret_cast<unsigned long long *>(ctr), (unsigned long long)v);
+}
+
+// One afterstate per lane (lane d of a 4-lane group = direction d), value by n-tuple gather, then a
+// width-4 shuffle argmax with the reference's tie rule (strict '>' scanning d = 0..3: lowest d wins).
+template <int N>
+__device__ __forceinline__ void best_move(const float *__restrict__ w, const LutGlobal &L, uint64_t board, int d,
+                                          bool run, uint64_t &best_after, uint32_t &best_gain, float &best_value,
+                                          int &best_dir, uint32_t &best_flags, uint32_t &n_valid)
+{
+    uint32_t gain = 0, fl = 0;
+    uint64_t after = move_dir(L, board, d, gain, fl);
+    const bool valid = run && (fl & 1u);
+    float v = valid ? evaluate<N>(w, after) : -INFINITY;
+    // a direction that would create 2^16 is kept valid here; the caller stops the game if it wins
+    float bv = v;
+    int bd = valid ? d : 4;                           // invalid lanes never win ties
+#pragma unroll
+    for (int off = 1; off < 4; off <<= 1) {
+        float ov = __shfl_xor_sync(FULL, bv, off, 4);
+        int od = __shfl_xor_sync(FULL, bd, off, 4);
+        if (od < 4 && (bd == 4 || ov > bv || (ov == bv && od < bd))) { bv = ov; bd = od; }
+    }
+    n_valid = __popc(__ballot_sync(FULL, valid) >> ((threadIdx.x & 31) & ~3) & 0xFu);
+    const int src = bd & 3;
+    best_after = shfl64(after, src, 4);
+    best_gain = __shfl_sync(FULL, gain, src, 4);
+    best_flags = __shfl_sync(FULL, fl, src, 4);
+    best_value = bv;
+    best_dir = bd;
+}
+
+template <int N>
+__global__ void __launch_bounds__(128)
+greedy_play_kernel(const float *__restrict__ w, const uint32_t *__restrict__ lut, b2048_games_t g, int max_steps,
+                   int limit_tile, int step_limit, b2048_replay_t rp, int has_replay, int8_t *__restrict__ trace_dir,
+                   float *__restrict__ trace_value, int64_t trace_len)
+{
+    const int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    const int64_t slot = t >> 2;
+    const int d = int(t & 3);
+    const bool in = slot < g.B;
+    LutGlobal L{lut};
+    uint64_t board = in ? g.board[slot] : 0;
+    uint32_t score = in ? g.score[slot] : 0;
+    uint32_t odo = in ? g.moves[slot] : 0;
+    uint32_t flags = in ? g.flags[slot] : B2048_F_DONE;
+    const uint64_t id = in ? g.game_id[slot] : 0;
+    bool run = in && !(flags & B2048_F_DONE);
+    uint32_t c_moves = 0, c_evals = 0, c_fin = 0, c_score = 0, c_msum = 0, c_ovf = 0;
+    for (int step = 0; step < max_steps; step++) {
+        if (!__any_sync(FULL, run)) break;
+        if (run) {
+            bool stop = game_over(board) || (limit_tile && max_tile(board) >= limit_tile) || int(odo) >= step_limit;
+            if (stop) {
+                flags |= B2048_F_DONE;
+                run = false;
+                if (d == 0) {
+                    c_fin++; c_score += score; c_msum += odo;
+                    atomicAdd(g.tile_hist + max_tile(board), 1u);
+                }
+            }
+        }
+        if (run && has_replay) {                                    // recorded spawns exhausted -> pause
+            if (int64_t(odo) >= rp.len || __ldg(rp.tile + slot * rp.len + odo) == 0) run = false;
+        }
+        uint64_t ba;
+        uint32_t bg, bf, nv;
+        float bv;
+        int bd;
+        best_move<N>(w, L, board, d, run, ba, bg, bv, bd, bf, nv);
+        if (run) {
+            if (bf & 2u) {                                          // 2^16 escape: flag + stop
+                flags |= B2048_F_DONE | B2048_F_OVERFLOW;
+                run = false;
+                if (d == 0) { c_fin++; c_score += score; c_msum += odo; c_ovf++; atomicAdd(g.tile_hist + 16, 1u); }
+            } else {
+                if (d == 0) {
+                    c_moves++; c_evals += nv;
+                    if (trace_dir && int64_t(odo) < trace_len) trace_dir[slot * trace_len + odo] = int8_t(bd);
+                    if (trace_value && int64_t(odo) < trace_len) trace_value[slot * trace_len + odo] = bv;
+                }
+                board = ba;
+                score += bg;
+                if (has_replay) {
+                    uint32_t tl = __ldg(rp.tile + slot * rp.len + odo);
+                    int sh = 4 * (15 - int(__ldg(rp.pos + slot * rp.len + odo) & 15));
+                    board = (board & ~(0xFULL << sh)) | (uint64_t(tl & 15u) << sh);
+                    odo++;
+                } else {
+                    odo++;
+                    Philox4 r = spawn_words(g.seed, id, odo, 0u);
+                    spawn_apply(board, r.x, r.y);
+                }
+            }
+        }
+    }
+    if (in && d == 0) {
+        g.board[slot] = board;
+        g.score[slot] = score;
+        g.moves[slot] = odo;
+        g.flags[slot] = uint8_t(flags);
+    }
+    warp_add_counter(g.counters + B2048_CTR_MOVES, c_moves);
+    warp_add_counter(g.counters + B2048_CTR_EVALS, c_evals);
+    warp_add_counter(g.counters + B2048_CTR_FINISHED, c_fin);
+    warp_add_counter(g.counters + B2048_CTR_SCORE_SUM, c_score);
+    warp_add_counter(g.counters + B2048_CTR_MOVES_SUM, c_msum);
+    warp_add_counter(g.counters + B2048_CTR_OVERFLOW, c_ovf);
+    warp_add_counter(g.counters + B2048_CTR_ACTIVE, (in && d == 0 && !(flags & B2048_F_DONE)) ? 1u : 0u);
+}
+
+// TD lock-step, phase A (see b2048.h).  4 lanes per slot.
+template <int N>
+__global__ void __launch_bounds__(128)
+td_phase_a_kernel(const float *__restrict__ w, const uint32_t *__restrict__ lut, b2048_games_t g, float alpha,
+                  uint64_t *__restrict__ upd_board, float *__restrict__ upd_dw, b2048_replay_t rp, int has_replay,
+                  int8_t *__restrict__ trace_dir, float *__restrict__ trace_value, float *__restrict__ trace_dw,
+                  int64_t trace_len)
+{
+    constexpr int F = num_feat(N);
+    const int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    const int64_t slot = t >> 2;
+    const int d = int(t & 3);
+    const bool in = slot < g.B;
+    LutGlobal L{lut};
+    uint64_t board = in ? g.board[slot] : 0;
+    uint32_t score = in ? g.score[slot] : 0;
+    uint32_t odo = in ? g.moves[slot] : 0;
+    uint32_t flags = in ? g.flags[slot] : B2048_F_DONE;
+    uint64_t id = in ? g.game_id[slot] : 0;
+    uint64_t state = in ? g.state[slot] : 0;
+    float old_label = in ? g.old_label[slot] : 0.0f;
+    bool run = in && !(flags & B2048_F_DONE);
+    if (run && has_replay && !game_over(board)) {
+        if (int64_t(odo) >= rp.len || __ldg(rp.tile + slot * rp.len + odo) == 0) run = false;   // spawns exhausted
+    }
+    const bool over = run && game_over(board);
+    uint64_t ba;
+    uint32_t bg, bf, nv;
+    float bv;
+    int bd;
+    best_move<N>(w, L, board, d, run && !over, ba, bg, bv, bd, bf, nv);
+    float dw = NAN;
+    uint64_t ub = 0;
+    uint32_t c_moves = 0, c_evals = 0, c_upd = 0, c_fin = 0, c_score = 0, c_msum = 0, c_ovf = 0;
+    if (run) {
+        const bool finished = over || (bf & 2u);
+        if (finished) {
+            if (flags & B2048_F_HAVE_STATE) {                        // r_learning.py:248-249
+                dw = __fdiv_rn(__fmul_rn(-old_label, alpha), float(F));
+                ub = state;
+            }
+            if (d == 0) {
+                c_fin++; c_score += score; c_msum += odo;
+                if (!over) c_ovf++;
+                atomicAdd(g.tile_hist + (over ? max_tile(board) : 16), 1u);
+                if (trace_dir && int64_t(odo) < trace_len) {
+                    trace_dir[slot * trace_len + odo] = -1;          // :247 sentinel
+                    if (trace_value) trace_value[slot * trace_len + odo] = 0.0f;
+                    if (trace_dw) trace_dw[slot * trace_len + odo] = dw;
+                }
+            }
+            if (has_replay) {
+                flags = (flags | B2048_F_DONE) & ~B2048_F_HAVE_STATE;
+                if (!over) flags |= B2048_F_OVERFLOW;
+            } else {                                                 // in-place restart
+                id += g.id_stride;
+                board = spawn_initial(g.seed, id);
+                score = 0; odo = 0; state = 0; old_label = 0.0f; flags = 0;
+            }
+        } else {
+            if (flags & B2048_F_HAVE_STATE) {                        // :238-241
+                float x = __fadd_rn(float(bg), bv);                  // (best_score - score) + best_value
+                x = __fsub_rn(x, old_label);
+                dw = __fdiv_rn(__fmul_rn(x, alpha), float(F));
+                ub = state;
+            }
+            if (d == 0) {
+                c_moves++; c_evals += nv;
+                if (trace_dir && int64_t(odo) < trace_len) {
+                    trace_dir[slot * trace_len + odo] = int8_t(bd);
+                    if (trace_value) trace_value[slot * trace_len + odo] = bv;
+                    if (trace_dw) trace_dw[slot * trace_len + odo] = dw;
+                }
+            }
+            board = ba;                                              // :242-245
+            score += bg;
+            state = ba;
+            old_label = bv;
+            flags |= B2048_F_HAVE_STATE;
+            if (has_replay) {                                        // :246 new_tile
+                uint32_t tl = __ldg(rp.tile + slot * rp.len + odo);
+                int sh = 4 * (15 - int(__ldg(rp.pos + slot * rp.len + odo) & 15));
+                board = (board & ~(0xFULL << sh)) | (uint64_t(tl & 15u) << sh);
+                odo++;
+            } else {
+                odo++;
+                Philox4 r = spawn_words(g.seed, id, odo, 0u);
+                spawn_apply(board, r.x, r.y);
+            }
+        }
+        if (d == 0 && !isnan(dw)) c_upd++;
+    }
+    if (in && d == 0) {
+        upd_board[slot] = ub;
+        upd_dw[slot] = dw;
+        if (run) {
+            g.board[slot] = board;
+            g.score[slot] = score;
+            g.moves[slot] = odo;
+            g.game_id[slot] = id;
+            g.state[slot] = state;
+            g.old_label[slot] = old_label;
+            g.flags[slot] = uint8_t(flags);
+        }
+    }
+    warp_add_counter(g.counters + B2048_CTR_MOVES, c_moves);
+    warp_add_counter(g.counters + B2048_CTR_EVALS, c_evals);
+    warp_add_counter(g.counters + B2048_CTR_UPDATES, c_upd);
+    warp_add_counter(g.counters + B2048_CTR_FINISHED, c_fin);
+    warp_add_counter(g.counters + B2048_CTR_SCORE_SUM, c_score);
+    warp_add_counter(g.counters + B2048_CTR_MOVES_SUM, c_msum);
+    warp_add_counter(g.counters + B2048_CTR_OVERFLOW, c_ovf);
+}
+
+__global__ void delta_apply_kernel(float *__restrict__ w, float *__restrict__ w_sync, float *__restrict__ delta,
+                                   const float *__restrict__ delta_sum, int64_t count)
+{
+    int64_t i = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) * 4;
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x * 4;
+    for (; i + 3 < count; i += stride) {
+        float4 s = *reinterpret_cast<const float4 *>(delta_sum + i);
+        float4 v = *reinterpret_cast<float4 *>(w_sync + i);
+        v.x = __fadd_rn(v.x, s.x); v.y = __fadd_rn(v.y, s.y); v.z = __fadd_rn(v.z, s.z); v.w = __fadd_rn(v.w, s.w);
+        *reinterpret_cast<float4 *>(w_sync + i) = v;
+        *reinterpret_cast<float4 *>(w + i) = v;
+        *reinterpret_cast<float4 *>(delta + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (int64_t q = count & ~int64_t(3); q < count; q++) {
+            float v = __fadd_rn(w_sync[q], delta_sum[q]);
+            w_sync[q] = v; w[q] = v; delta[q] = 0.f;
+        }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side dispatch helpers
+// ------------------------------------------------------------------------------------------------
+#define DISPATCH_N(n, ...)                               \
+    switch (n) {                                         \
+    case 2: { constexpr int N = 2; __VA_ARGS__; } break; \
+    case 3: { constexpr int N = 3; __VA_ARGS__; } break; \
+    case 4: { constexpr int N = 4; __VA_ARGS__; } break; \
+    case 5: { constexpr int N = 5; __VA_ARGS__; } break; \
+    case 6: { constexpr int N = 6; __VA_ARGS__; } break; \
+    default: return B2048_EINVAL;                        \
+    }
+
+inline int key_bits(int n)
+{
+    int64_t nw = table_offset(n, num_feat(n));
+    int b = 1;
+    while ((int64_t(1) << b) < nw + 1) b++;          // +1: the 0xFFFFFFFF sentinel must sort last
+    return b;
+}
+
+struct DetLayout {
+    int64_t M;          // keys
+    int nblocks;
+    size_t keys_a, keys_b, vals_a, vals_b, hist, acc, cnt, total;
+};
+
+inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+inline DetLayout det_layout(int n, int64_t m)
+{
+    DetLayout L{};
+    L.M = m * 8 * num_feat(n);
+    L.nblocks = int(cdiv(L.M, SORT_TILE));
+    size_t kb = align256(size_t(L.M) * 4);
+    size_t o = 0;
+    L.keys_a = o; o += kb;
+    L.keys_b = o; o += kb;
+    L.vals_a = o; o += kb;
+    L.vals_b = o; o += kb;
+    L.hist = o; o += align256(size_t(256) * size_t(L.nblocks > 0 ? L.nblocks : 1) * 4);
+    L.total = o;
+    return L;
+}
+
+template <int BITS>
+int radix_pass(const uint32_t *kin, const uint32_t *vin, uint32_t *kout, uint32_t *vout, uint32_t *hist, int64_t M,
+               int shift, int nblocks, cudaStream_t st)
+{
+    radix_hist_kernel<BITS><<<nblocks, SORT_THREADS, 0, st>>>(kin, M, shift, hist, nblocks);
+    scan_kernel<<<1, 1024, 0, st>>>(hist, int64_t(1 << BITS) * nblocks);
+    radix_scatter_kernel<BITS><<<nblocks, SORT_THREADS, 0, st>>>(kin, vin, kout, vout, hist, M, shift, nblocks);
+    return launch_status();
+}
+
+int td_update_impl(int n, float *weights, float *delta, const uint64_t *boards, const float *dw, int64_t m, int mode,
+                   void *work, size_t work_bytes, cudaStream_t st)
+{
+    if (m == 0) return 0;
+    const bool det = mode & B2048_UPD_DETERMINISTIC, mean = mode & B2048_UPD_MEAN;
+    const int64_t threads = m * 8;
+    const int blk = 128;
+    const unsigned grid = unsigned(cdiv(threads, blk));
+    if (!det && !mean) {
+        DISPATCH_N(n, td_update_atomic_sum_kernel<N><<<grid, blk, 0, st>>>(weights, delta, boards, dw, m));
+        return launch_status();
+    }
+    if (!det) {
+        // workspace = acc (float) + cnt (uint32), both num_weights long and all-zero between calls
+        const int64_t nw = table_offset(n, num_feat(n));
+        if (!work || work_bytes < size_t(nw) * 8) return B2048_EWORK;
+        float *acc = reinterpret_cast<float *>(work);
+        uint32_t *cnt = reinterpret_cast<uint32_t *>(acc + nw);
+        DISPATCH_N(n, td_update_mean_accum_kernel<N><<<grid, blk, 0, st>>>(acc, cnt, boards, dw, m));
+        DISPATCH_N(n, td_update_mean_apply_kernel<N><<<grid, blk, 0, st>>>(weights, delta, acc, cnt, boards, dw, m));
+        return launch_status();
+    }
+    DetLayout L = det_layout(n, m);
+    if (!work || work_bytes < L.total) return B2048_EWORK;
+    unsigned char *base = reinterpret_cast<unsigned char *>(work);
+    uint32_t *ka = reinterpret_cast<uint32_t *>(base + L.keys_a), *kb = reinterpret_cast<uint32_t *>(base + L.keys_b);
+    uint32_t *va = reinterpret_cast<uint32_t *>(base + L.vals_a), *vb = reinterpret_cast<uint32_t *>(base + L.vals_b);
+    uint32_t *hist = reinterpret_cast<uint32_t *>(base + L.hist);
+    DISPATCH_N(n, td_keys_kernel<N><<<grid, blk, 0, st>>>(boards, dw, m, ka, va));
+    const int bits = key_bits(n);
+    const int passes = (bits + 7) / 8;
+    const int per = (bits + passes - 1) / passes;       // digit width 5..8, equal for all passes
+    int shift = 0, rc = 0;
+    for (int p = 0; p < passes && !rc; p++, shift += per) {
+        switch (per) {
+        case 8: rc = radix_pass<8>(ka, va, kb, vb, hist, L.M, shift, L.nblocks, st); break;
+        case 7: rc = radix_pass<7>(ka, va, kb, vb, hist, L.M, shift, L.nblocks, st); break;
+        case 6: rc = radix_pass<6>(ka, va, kb, vb, hist, L.M, shift, L.nblocks, st); break;
+        default: rc = radix_pass<5>(ka, va, kb, vb, hist, L.M, shift, L.nblocks, st); break;
+        }
+        uint32_t *tk = ka; ka = kb; kb = tk;
+        uint32_t *tv = va; va = vb; vb = tv;
+    }
+    if (rc) return rc;
+    td_segment_apply_kernel<<<unsigned(cdiv(L.M, 256)), 256, 0, st>>>(weights, delta, ka, va, dw, L.M, mean ? 1 : 0);
+    return launch_status();
+}
+
+bool games_ok(const b2048_games_t *g)
+{
+    return g && g->B >= 0 && g->board && g->score && g->moves && g->game_id && g->state && g->old_label && g->flags &&
+           g->counters && g->tile_hist;
+}
+
+}   // namespace
+
+// ================================================================================================
+// C-ABI
+// ================================================================================================
+extern "C" {
+
+int b2048_abi_version(void) { return B2048_ABI_VERSION; }
+
+const char *b2048_strerror(int code)
+{
+    if (code == 0) return "ok";
+    if (code == B2048_EINVAL) return "b2048: invalid argument";
+    if (code == B2048_ENOTSUP) return "b2048: not supported";
+    if (code == B2048_EWORK) return "b2048: workspace too small";
+    if (code > 0) return cudaGetErrorString(cudaError_t(code));
+    return "b2048: unknown error";
+}
+
+int b2048_num_feat(int n) { return num_feat(n); }
+
+int64_t b2048_table_offset(int n, int i)
+{
+    int F = num_feat(n);
+    if (F < 0 || i < 0 || i > F) return -1;
+    return table_offset(n, i);
+}
+
+int64_t b2048_num_weights(int n)
+{
+    int F = num_feat(n);
+    return F < 0 ? -1 : table_offset(n, F);
+}
+
+int b2048_pack(const int32_t *rows, uint64_t *boards, int64_t m, b2048_stream_t stream)
+{
+    if (m < 0 || (m && (!rows || !boards))) return B2048_EINVAL;
+    if (!m) return 0;
+    pack_kernel<<<unsigned(cdiv(m, 256)), 256, 0, S(stream)>>>(rows, boards, m);
+    return launch_status();
+}
+
+int b2048_unpack(const uint64_t *boards, int32_t *rows, int64_t m, b2048_stream_t stream)
+{
+    if (m < 0 || (m && (!rows || !boards))) return B2048_EINVAL;
+    if (!m) return 0;
+    unpack_kernel<<<unsigned(cdiv(m, 256)), 256, 0, S(stream)>>>(boards, rows, m);
+    return launch_status();
+}
+
+int b2048_lut_build(uint32_t *lut, b2048_stream_t stream)
+{
+    if (!lut) return B2048_EINVAL;
+    lut_build_kernel<<<B2048_LUT_ENTRIES / 256, 256, 0, S(stream)>>>(lut);
+    return launch_status();
+}
+
+int b2048_move4(const uint32_t *lut, const uint64_t *boards, int64_t m, uint64_t *after, uint32_t *gain,
+                uint8_t *flags, uint8_t *over, b2048_stream_t stream)
+{
+    if (m < 0 || !lut || (m && (!boards || !after || !gain || !flags))) return B2048_EINVAL;
+    if (!m) return 0;
+    move4_kernel<<<unsigned(cdiv(m, 256)), 256, 0, S(stream)>>>(lut, boards, m, after, gain, flags, over);
+    return launch_status();
+}
+
+int b2048_board_stats(const uint64_t *boards, int64_t m, uint8_t *stats, uint16_t *empty_mask, b2048_stream_t stream)
+{
+    if (m < 0 || (m && !boards)) return B2048_EINVAL;
+    if (!m) return 0;
+    board_stats_kernel<<<unsigned(cdiv(m, 256)), 256, 0, S(stream)>>>(boards, m, stats, empty_mask);
+    return launch_status();
+}
+
+int b2048_spawn_philox(uint64_t *boards, int64_t m, uint64_t seed, const uint64_t *game_id, const uint32_t *move_no,
+                       uint16_t *spawn, b2048_stream_t stream)
+{
+    if (m < 0 || (m && (!boards || !game_id || !move_no))) return B2048_EINVAL;
+    if (!m) return 0;
+    spawn_philox_kernel<<<unsigned(cdiv(m, 256)), 256, 0, S(stream)>>>(boards, m, seed, game_id, move_no, spawn);
+    return launch_status();
+}
+
+int b2048_spawn_initial(uint64_t *boards, int64_t m, uint64_t seed, uint64_t first_id, uint64_t id_step,
+                        b2048_stream_t stream)
+{
+    if (m < 0 || (m && !boards)) return B2048_EINVAL;
+    if (!m) return 0;
+    spawn_initial_kernel<<<unsigned(cdiv(m, 256)), 256, 0, S(stream)>>>(boards, m, seed, first_id, id_step);
+    return launch_status();
+}
+
+int b2048_spawn_replay(uint64_t *boards, int64_t m, const uint8_t *tile, const uint8_t *pos, b2048_stream_t stream)
+{
+    if (m < 0 || (m && (!boards || !tile || !pos))) return B2048_EINVAL;
+    if (!m) return 0;
+    spawn_replay_kernel<<<unsigned(cdiv(m, 256)), 256, 0, S(stream)>>>(boards, m, tile, pos);
+    return launch_status();
+}
+
+int b2048_sweep(const uint32_t *lut, const uint64_t *boards, int64_t m, uint64_t seed, uint64_t first_index,
+                uint64_t *after, uint32_t *gain, uint8_t *flags, uint64_t *spawned, b2048_stream_t stream)
+{
+    if (m < 0 || !lut || (m && (!boards || !after || !gain || !flags))) return B2048_EINVAL;
+    if (!m) return 0;
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SWEEP_SMEM));
+        if (e != cudaSuccess) return int(e);
+        attr_set[dev] = true;
+    }
+    int64_t want = cdiv(m, SWEEP_THREADS);
+    unsigned grid = unsigned(want < sm_count() ? want : sm_count());
+    sweep_kernel<<<grid, SWEEP_THREADS, SWEEP_SMEM, S(stream)>>>(lut, boards, m, seed, first_index, after, gain, flags,
+                                                                 spawned);
+    return launch_status();
+}
+
+int b2048_features(int n, const uint64_t *boards, int64_t m, int32_t *feat, b2048_stream_t stream)
+{
+    if (m < 0 || num_feat(n) < 0 || (m && (!boards || !feat))) return B2048_EINVAL;
+    if (!m) return 0;
+    DISPATCH_N(n, features_kernel<N><<<unsigned(cdiv(m, 128)), 128, 0, S(stream)>>>(boards, m, feat));
+    return launch_status();
+}
+
+int b2048_evaluate(int n, const float *weights, const uint64_t *boards, int64_t m, float *value, b2048_stream_t stream)
+{
+    if (m < 0 || num_feat(n) < 0 || !weights || (m && (!boards || !value))) return B2048_EINVAL;
+    if (!m) return 0;
+    DISPATCH_N(n, evaluate_kernel<N><<<unsigned(cdiv(m, 128)), 128, 0, S(stream)>>>(weights, boards, m, value));
+    return launch_status();
+}
+
+size_t b2048_td_update_workspace(int n, int64_t m, int mode)
+{
+    if (num_feat(n) < 0 || m < 0) return 0;
+    if (mode & B2048_UPD_DETERMINISTIC) return det_layout(n, m).total;
+    if (mode & B2048_UPD_MEAN) return size_t(table_offset(n, num_feat(n))) * 8;
+    return 0;
+}
+
+int b2048_td_update(int n, float *weights, float *delta, const uint64_t *boards, const float *dw, int64_t m, int mode,
+                    void *work, size_t work_bytes, b2048_stream_t stream)
+{
+    if (m < 0 || num_feat(n) < 0 || !weights || (m && (!boards || !dw)) || (mode & ~3)) return B2048_EINVAL;
+    return td_update_impl(n, weights, delta, boards, dw, m, mode, work, work_bytes, S(stream));
+}
+
+int b2048_games_init(const b2048_games_t *g, uint64_t first_id, int reset_counters, b2048_stream_t stream)
+{
+    if (!games_ok(g)) return B2048_EINVAL;
+    int64_t threads = g->B > 32 ? g->B : 32;
+    games_init_kernel<<<unsigned(cdiv(threads, 256)), 256, 0, S(stream)>>>(*g, first_id, reset_counters);
+    return launch_status();
+}
+
+int b2048_greedy_play(int n, const float *weights, const uint32_t *lut, const b2048_games_t *g, int max_steps,
+                      int limit_tile, int step_limit, const b2048_replay_t *replay, int8_t *trace_dir,
+                      float *trace_value, int64_t trace_len, b2048_stream_t stream)
+{
+    if (!games_ok(g) || num_feat(n) < 0 || !weights || !lut || max_steps < 0) return B2048_EINVAL;
+    if (replay && (!replay->tile || !replay->pos || replay->len < 0)) return B2048_EINVAL;
+    if (g->B == 0) return 0;
+    cudaError_t e = cudaMemsetAsync(g->counters + B2048_CTR_ACTIVE, 0, sizeof(uint64_t), S(stream));
+    if (e != cudaSuccess) return int(e);
+    b2048_replay_t rp = replay ? *replay : b2048_replay_t{nullptr, nullptr, 0};
+    unsigned grid = unsigned(cdiv(g->B * 4, 128));
+    DISPATCH_N(n, greedy_play_kernel<N><<<grid, 128, 0, S(stream)>>>(weights, lut, *g, max_steps, limit_tile, step_limit,
+                                                                     rp, replay ? 1 : 0, trace_dir, trace_value,
+                                                                     trace_len));
+    return launch_status();
+}
+
+int b2048_td_step(int n, float *weights, float *delta, const uint32_t *lut, const b2048_games_t *g, float alpha,
+                  int mode, uint64_t *upd_board, float *upd_dw, void *work, size_t work_bytes,
+                  const b2048_replay_t *replay, int8_t *trace_dir, float *trace_value, float *trace_dw,
+                  int64_t trace_len, b2048_stream_t stream)
+{
+    if (!games_ok(g) || num_feat(n) < 0 || !weights || !lut || !upd_board || !upd_dw || (mode & ~3)) return B2048_EINVAL;
+    if (replay && (!replay->tile || !replay->pos || replay->len < 0)) return B2048_EINVAL;
+    if (g->B == 0) return 0;
+    b2048_replay_t rp = replay ? *replay : b2048_replay_t{nullptr, nullptr, 0};
+    unsigned grid = unsigned(cdiv(g->B * 4, 128));
+    DISPATCH_N(n, td_phase_a_kernel<N><<<grid, 128, 0, S(stream)>>>(weights, lut, *g, alpha, upd_board, upd_dw, rp,
+                                                                    replay ? 1 : 0, trace_dir, trace_value, trace_dw,
+                                                                    trace_len));
+    int rc = launch_status();
+    if (rc) return rc;
+    return td_update_impl(n, weights, delta, upd_board, upd_dw, g->B, mode, work, work_bytes, S(stream));
+}
+
+int b2048_td_run(int n, float *weights, float *delta, const uint32_t *lut, const b2048_games_t *g, float alpha,
+                 int mode, int steps, uint64_t *upd_board, float *upd_dw, void *work, size_t work_bytes,
+                 b2048_stream_t stream)
+{
+    if (steps < 0) return B2048_EINVAL;
+    for (int s = 0; s < steps; s++) {
+        int rc = b2048_td_step(n, weights, delta, lut, g, alpha, mode, upd_board, upd_dw, work, work_bytes, nullptr,
+                               nullptr, nullptr, nullptr, 0, stream);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+int b2048_delta_apply(float *weights, float *w_sync, float *delta, const float *delta_sum, int64_t count,
+                      b2048_stream_t stream)
+{
+    if (count < 0 || (count && (!weights || !w_sync || !delta || !delta_sum))) return B2048_EINVAL;
+    if (!count) return 0;
+    int64_t want = cdiv(count, 4 * 256);
+    int64_t cap = int64_t(sm_count()) * 8;
+    delta_apply_kernel<<<unsigned(want < cap ? want : cap), 256, 0, S(stream)>>>(weights, w_sync, delta, delta_sum, count);
+    return launch_status();
+}
+
+}   // extern "C"

@@ -1,0 +1,211 @@
+/*
+ * b2048.h -- C-ABI of the B200-native 2048 / n-tuple hot path (libb2048.so, sm_100a).
+ *
+ * The reference (abachurin/2048) is pure Python and has no FFI layer; its boundary for this path
+ * is the class surface of game2048/game_logic.py (Game) and game2048/r_learning.py (QAgent).
+ * Every entry point below names the reference function (file:line under /root/reference) whose
+ * work it performs for a whole batch.  The Python binding a maintainer would add is a ctypes stub
+ * (INTEGRATION.md); 2048_b200/game2048/cabi.py is that stub.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name starts with
+ *     h_; the caller allocates and frees everything, the library keeps no mutable global state
+ *     (re-entrant, callable from any host thread);
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on that stream;
+ *   - return value: 0 = ok, < 0 = B2048_E* argument error, > 0 = cudaError_t of the launch;
+ *   - packed board: uint64, cell (r,c) = nibble at bit 4*(15-4r-c) holding the exponent
+ *     (0 = empty, k = tile 2^k), i.e. the 16 hex digits read in row-major order
+ *     (reference board: 4x4 int32 exponents, game_logic.py:41-45,62);
+ *   - 2^16 escape: a nibble cannot hold exponent 16.  A move that would create a 2^16 tile sets an
+ *     overflow bit and stores that cell saturated at 15; game loops treat the game as finished and
+ *     count it in B2048_CTR_OVERFLOW (the reference raises KeyError there, game_logic.py:129);
+ *   - directions: 0=left 1=up 2=right 3=down (game_logic.py:50);
+ *   - weights: ONE contiguous float32 buffer, table i of agent n at b2048_table_offset(n, i), the
+ *     order of the reference's weights[i] list (r_learning.py:136-149).
+ */
+#ifndef B2048_H
+#define B2048_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2048_ABI_VERSION 1
+
+#define B2048_EINVAL (-1)   /* bad argument (NULL pointer, negative size, unknown n) */
+#define B2048_ENOTSUP (-2)  /* not supported on this device / configuration */
+#define B2048_EWORK (-3)    /* workspace too small */
+
+typedef void *b2048_stream_t;
+
+/* ---- library / layout queries (host only, no device work) -------------------------------- */
+int b2048_abi_version(void);
+const char *b2048_strerror(int code);
+/* QAgent.parameter_shape, r_learning.py:88: 24/52/17/21/33 features for n = 2..6; -1 otherwise */
+int b2048_num_feat(int n);
+/* first weight of table i (i = num_feat gives the total), r_learning.py:136-149 */
+int64_t b2048_table_offset(int n, int i);
+int64_t b2048_num_weights(int n);
+
+/* ---- (1) packed boards -------------------------------------------------------------------- */
+/* rows: int32 [m,16] row-major exponents  <->  boards: uint64 [m] */
+int b2048_pack(const int32_t *rows, uint64_t *boards, int64_t m, b2048_stream_t stream);
+int b2048_unpack(const uint64_t *boards, int32_t *rows, int64_t m, b2048_stream_t stream);
+
+/* ---- (2) moves ---------------------------------------------------------------------------- */
+/* create_table, game_logic.py:18-39.  lut: uint32 [65536], key = the packed 16-bit line:
+ *   bits 0-15 line after "slide+merge left"; bits 16-19 / 20-23 exponents x of the (up to two)
+ *   merges (score += 2^(x+1) each, 0 = none); bit 24 changed; bit 25 overflow (a 2^16 was made). */
+#define B2048_LUT_ENTRIES 65536
+int b2048_lut_build(uint32_t *lut, b2048_stream_t stream);
+
+/* Game.pre_move for all four directions, game_logic.py:123-142, plus game_over (:109-110):
+ *   after [m,4] afterstates, gain [m,4] merge score of the move (new_score - score),
+ *   flags [m]: bit d = direction d changed the board, bit 4+d = direction d overflowed,
+ *   over [m] (may be NULL): 1 iff no empty cell and no equal neighbours. */
+int b2048_move4(const uint32_t *lut, const uint64_t *boards, int64_t m, uint64_t *after, uint32_t *gain,
+                uint8_t *flags, uint8_t *over, b2048_stream_t stream);
+
+/* Game.empty / empty_count / adjacent_pair_count / game_over, game_logic.py:96-110, and max tile.
+ * stats: uint8 [m,4] = (empty_count, adjacent_pair_count, game_over, max exponent);
+ * empty_mask: uint16 [m], bit p set iff flat cell p = 4r+c is empty (row-major order). NULL ok. */
+int b2048_board_stats(const uint64_t *boards, int64_t m, uint8_t *stats, uint16_t *empty_mask,
+                      b2048_stream_t stream);
+
+/* ---- (3) new tiles ------------------------------------------------------------------------- */
+/* Game.create_new_tile / new_tile, game_logic.py:112-121, from a counter-based Philox4x32-10 stream
+ * instead of Python's `random`: key = seed, counter = (id_lo, id_hi, move_no, purpose 0);
+ * tile = 2 ("4") iff mulhi(w0,10) == 0 else 1; cell = the mulhi(w1, n_empty)-th empty cell in
+ * row-major order.  boards in/out; spawn (may be NULL) receives (tile << 8) | flat cell, 0xFFFF if
+ * the board was full (the reference would raise IndexError). */
+int b2048_spawn_philox(uint64_t *boards, int64_t m, uint64_t seed, const uint64_t *game_id,
+                       const uint32_t *move_no, uint16_t *spawn, b2048_stream_t stream);
+/* Game.__init__, game_logic.py:61-66: empty board + two spawns (words 0,1 then 2,3 of move_no 0);
+ * game ids are first_id + i*id_step. */
+int b2048_spawn_initial(uint64_t *boards, int64_t m, uint64_t seed, uint64_t first_id, uint64_t id_step,
+                        b2048_stream_t stream);
+/* replay mode, Game.replay game_logic.py:259-260: boards[i] cell pos[i] := tile[i]; entries with
+ * tile == 0 are skipped (ragged batches). */
+int b2048_spawn_replay(uint64_t *boards, int64_t m, const uint8_t *tile, const uint8_t *pos,
+                       b2048_stream_t stream);
+
+/* BASELINE config 5: move4 + a Philox spawn on every changed, non-overflowing afterstate, one pass.
+ * spawn stream: counter = (index_lo, index_hi, d>>1, purpose 1), words 2(d&1), 2(d&1)+1, with
+ * index = first_index + i.  spawned [m,4] (NULL = no spawn pass).  Row LUTs are staged in shared
+ * memory by a persistent grid. */
+int b2048_sweep(const uint32_t *lut, const uint64_t *boards, int64_t m, uint64_t seed, uint64_t first_index,
+                uint64_t *after, uint32_t *gain, uint8_t *flags, uint64_t *spawned, b2048_stream_t stream);
+
+/* ---- (4) n-tuple agent ---------------------------------------------------------------------- */
+/* f_2 .. f_6, r_learning.py:17-69: feat int32 [m, num_feat(n)] table indices in table order */
+int b2048_features(int n, const uint64_t *boards, int64_t m, int32_t *feat, b2048_stream_t stream);
+/* QAgent.evaluate, r_learning.py:202-203: value[i] = sum over tables, float32, table order */
+int b2048_evaluate(int n, const float *weights, const uint64_t *boards, int64_t m, float *value,
+                   b2048_stream_t stream);
+/* QAgent.update, r_learning.py:207-214, for m (board, dw) entries sharing one table set: for the 8
+ * D4 images of each board, weights[table][index] += dw.  Entries whose dw is NaN are skipped.
+ * mode = execution | rule:
+ *   B2048_UPD_ATOMIC         red.global.add.f32, unordered
+ *   B2048_UPD_DETERMINISTIC  (key, entry) pairs are radix-sorted by key (stable), each key's
+ *                            contributions are summed in ascending entry order (sequential float32
+ *                            from 0) and applied once -> run-to-run bit-identical
+ *   B2048_UPD_SUM            w[k] += S[k], S[k] = sum of the contributions to key k (the reference
+ *                            rule; exactly QAgent.update when m == 1)
+ *   B2048_UPD_MEAN           w[k] += S[k] / G[k], G[k] = number of DISTINCT entries contributing to
+ *                            k: the batched rule that stays stable at the reference's alpha when
+ *                            many games hit the same key in one lock-step; == SUM at m == 1
+ * delta (may be NULL) receives the same increments as weights (multi-GPU delta buffer).
+ * work: b2048_td_update_workspace(n, m, mode) bytes; for ATOMIC|MEAN it must be all-zero on first
+ * use and is left all-zero by every call. */
+#define B2048_UPD_ATOMIC 0
+#define B2048_UPD_DETERMINISTIC 1
+#define B2048_UPD_SUM 0
+#define B2048_UPD_MEAN 2
+size_t b2048_td_update_workspace(int n, int64_t m, int mode);
+int b2048_td_update(int n, float *weights, float *delta, const uint64_t *boards, const float *dw, int64_t m, int mode,
+                    void *work, size_t work_bytes, b2048_stream_t stream);
+
+/* ---- fused game loops ------------------------------------------------------------------------ */
+/* Device-resident state of B game slots (structure of arrays; every pointer is a device pointer). */
+typedef struct b2048_games {
+    int64_t B;            /* slots */
+    uint64_t *board;      /* [B] current board (after the spawn) */
+    uint32_t *score;      /* [B] Game.score */
+    uint32_t *moves;      /* [B] Game.odometer */
+    uint64_t *game_id;    /* [B] Philox stream id of the game in the slot */
+    uint64_t *state;      /* [B] TD: previous afterstate (r_learning.py:245 `state`) */
+    float *old_label;     /* [B] TD: its value at the time (r_learning.py:245 `old_label`) */
+    uint8_t *flags;       /* [B] B2048_F_* */
+    uint64_t *counters;   /* [B2048_CTR_COUNT] accumulated by the kernels */
+    uint32_t *tile_hist;  /* [17] finished games by max exponent */
+    uint64_t seed;        /* Philox key */
+    uint64_t id_stride;   /* TD in-place restart: game_id += id_stride (total slots over all ranks) */
+} b2048_games_t;
+
+#define B2048_F_HAVE_STATE 1u /* TD: state/old_label valid */
+#define B2048_F_DONE 2u       /* greedy: game finished (game over, limit tile, or overflow) */
+#define B2048_F_OVERFLOW 4u   /* a 2^16 tile would have been created */
+
+enum {
+    B2048_CTR_MOVES = 0,    /* committed moves */
+    B2048_CTR_EVALS = 1,    /* evaluate() calls (valid afterstates scored) */
+    B2048_CTR_UPDATES = 2,  /* update() calls (8*num_feat weight RMWs each) */
+    B2048_CTR_FINISHED = 3, /* games finished */
+    B2048_CTR_SCORE_SUM = 4,
+    B2048_CTR_MOVES_SUM = 5,
+    B2048_CTR_OVERFLOW = 6,
+    B2048_CTR_ACTIVE = 7,   /* greedy_play: slots still playing after the call (overwritten) */
+    B2048_CTR_COUNT = 8
+};
+
+/* Fresh games in every slot: ids first_id + i, Game.__init__ spawns, zero score/moves/flags;
+ * zeroes counters and tile_hist when reset_counters != 0. */
+int b2048_games_init(const b2048_games_t *g, uint64_t first_id, int reset_counters, b2048_stream_t stream);
+
+/* Game.trial_run at depth 0, game_logic.py:150-183, for every slot that is not DONE: up to
+ * max_steps moves per slot in ONE launch (each game advances independently; weights are read-only).
+ * limit_tile as in trial_run (exponent; 0 = none); step_limit = total odometer cap (100000 there).
+ * replay == NULL: Philox spawns.  Otherwise replay mode: tile/pos are [B, replay_len] recorded
+ * spawns (tile 0 = exhausted -> slot stops, stays not DONE), indexed by the slot's odometer.
+ * trace_dir/trace_value (may be NULL): [B, trace_len] chosen direction / its value per move. */
+typedef struct b2048_replay {
+    const uint8_t *tile;  /* [B, len] */
+    const uint8_t *pos;   /* [B, len] flat cell 4r+c */
+    int64_t len;
+} b2048_replay_t;
+int b2048_greedy_play(int n, const float *weights, const uint32_t *lut, const b2048_games_t *g, int max_steps,
+                      int limit_tile, int step_limit, const b2048_replay_t *replay, int8_t *trace_dir,
+                      float *trace_value, int64_t trace_len, b2048_stream_t stream);
+
+/* One lock-step of QAgent.episode (r_learning.py:224-252) for all B slots, two launches:
+ *   phase A (every slot, weights W_t read-only): game over -> terminal dw = -old_label*alpha/F
+ *     (:247-249), statistics, in-place restart; else best afterstate by strict '>' over d=0..3
+ *     (:229-237), dw = (gain + best_value - old_label)*alpha/F if a previous afterstate exists
+ *     (:238-241), commit, remember (state, old_label) (:242-245), spawn (:246).
+ *   phase B: b2048_td_update(previous state, dw) over the B slots (mode, work as there, m = B).
+ * upd_board [B], upd_dw [B] are scratch owned by the caller (dw = NaN marks "no update").
+ * delta (may be NULL): second accumulation buffer of the same shape as weights that receives the
+ * same updates (multi-GPU: allreduced every K steps, then b2048_delta_apply).
+ * replay / trace as in b2048_greedy_play (trace_len entries per slot, indexed by odometer; replay
+ * mode never restarts a slot: a finished slot gets DONE after its terminal update). */
+int b2048_td_step(int n, float *weights, float *delta, const uint32_t *lut, const b2048_games_t *g, float alpha,
+                  int mode, uint64_t *upd_board, float *upd_dw, void *work, size_t work_bytes,
+                  const b2048_replay_t *replay, int8_t *trace_dir, float *trace_value, float *trace_dw,
+                  int64_t trace_len, b2048_stream_t stream);
+/* `steps` lock-steps enqueued back to back (no host work in between). */
+int b2048_td_run(int n, float *weights, float *delta, const uint32_t *lut, const b2048_games_t *g, float alpha,
+                 int mode, int steps, uint64_t *upd_board, float *upd_dw, void *work, size_t work_bytes,
+                 b2048_stream_t stream);
+
+/* multi-GPU weight sync: after allreduce(sum) of every rank's delta into delta_sum,
+ * w_sync += delta_sum; weights = w_sync; delta = 0  -- one fused pass, replicas end bit-identical. */
+int b2048_delta_apply(float *weights, float *w_sync, float *delta, const float *delta_sum, int64_t count,
+                      b2048_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2048_H */

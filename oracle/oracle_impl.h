@@ -1,0 +1,356 @@
+/*
+ * oracle/oracle_impl.h -- TEST INFRASTRUCTURE ONLY (see oracle.c header).
+ *
+ * Precision-generic half of the oracle.  oracle.c includes this file twice:
+ *   REAL=double, SUF=f64  -> the reference's arithmetic (Python floats are float64)
+ *   REAL=float,  SUF=f32  -> the same statements in float32, i.e. the arithmetic the
+ *                            device path computes in, so that the CUDA deterministic
+ *                            mode can be compared BIT-EXACT with this restatement.
+ * Every function cites the reference file:line (relative to /root/reference) it follows.
+ */
+
+#define CAT_(a, b) a##_##b
+#define CAT(a, b) CAT_(a, b)
+#define FN(name) CAT(name, SUF)
+
+/* r_learning.py:202-203  evaluate: sum(weights[i][f_i(row)]) in table order, starting from 0. */
+REAL FN(orc_evaluate)(int n, const REAL *w, const int32_t *row)
+{
+    int32_t f[ORC_MAX_FEAT];
+    int F = orc_features(n, row, f);
+    REAL v = 0;
+    for (int i = 0; i < F; i++) v = v + w[orc_table_offset(n, i) + f[i]];
+    return v;
+}
+
+/* r_learning.py:207-214  update: the 8 D4 images in the reference's order
+ * r, r^T, R r, (R r)^T, ...  with R = rot90(transpose(transpose(.))) = rot90. */
+void FN(orc_update)(int n, REAL *w, const int32_t *row_in, REAL dw)
+{
+    int32_t row[16], t[16], f[ORC_MAX_FEAT];
+    memcpy(row, row_in, sizeof row);
+    for (int k = 0; k < 4; k++) {
+        int F = orc_features(n, row, f);
+        for (int i = 0; i < F; i++) w[orc_table_offset(n, i) + f[i]] += dw;
+        orc_transpose(row, t);                       /* :211 row = np.transpose(row) */
+        F = orc_features(n, t, f);
+        for (int i = 0; i < F; i++) w[orc_table_offset(n, i) + f[i]] += dw;
+        orc_transpose(t, row);                       /* :214 np.rot90(np.transpose(row)) */
+        orc_rot90(row, 1, t);
+        memcpy(row, t, sizeof row);
+    }
+}
+
+/* The (table offset + index) keys one update() touches, in the reference's order (8*F of them). */
+int FN(orc_update_keys)(int n, const int32_t *row_in, int64_t *keys)
+{
+    int32_t row[16], t[16], f[ORC_MAX_FEAT];
+    int m = 0;
+    memcpy(row, row_in, sizeof row);
+    for (int k = 0; k < 4; k++) {
+        int F = orc_features(n, row, f);
+        for (int i = 0; i < F; i++) keys[m++] = orc_table_offset(n, i) + f[i];
+        orc_transpose(row, t);
+        F = orc_features(n, t, f);
+        for (int i = 0; i < F; i++) keys[m++] = orc_table_offset(n, i) + f[i];
+        orc_transpose(t, row);
+        orc_rot90(row, 1, t);
+        memcpy(row, t, sizeof row);
+    }
+    return m;
+}
+
+/* r_learning.py:229-237 (== game_logic.py:150-161 at depth 0): scan d = 0..3, skip unchanged
+ * directions, strict '>' so the lowest direction wins ties.  Returns the action (0 if none valid,
+ * like the reference's initial 'action = 0'), and the best afterstate/score/value. */
+static int FN(best_move)(int n, const REAL *w, const int32_t *row, int64_t score,
+                         int32_t *best_row, int64_t *best_score, REAL *best_value, int *n_valid)
+{
+    int action = 0, any = 0;
+    REAL bv = -INFINITY;
+    for (int d = 0; d < 4; d++) {
+        int32_t nr[16];
+        int64_t ns;
+        int ch = orc_pre_move(row, score, d, nr, &ns);
+        if (ch < 0) return -1;
+        if (ch) {
+            REAL v = FN(orc_evaluate)(n, w, nr);
+            any++;
+            if (v > bv) {
+                action = d; bv = v;
+                memcpy(best_row, nr, sizeof nr);
+                *best_score = ns;
+            }
+        }
+    }
+    *best_value = bv;
+    if (n_valid) *n_valid = any;
+    return action;
+}
+
+/*
+ * r_learning.py:224-252  QAgent.episode, teacher-forced: the spawns come from the recorded
+ * `tiles` list (game_logic.py:112-121 recorded at :121) instead of Python's `random`.
+ *   start[16]            the reference game's starting_position (game_logic.py:66)
+ *   tiles[3*k + 0..2]    (tile, i, j) of the k-th recorded spawn
+ * Outputs (each sized for n_tiles + 1 entries): moves (with the -1 sentinel, :247), values
+ * (best_value per step), dws (the dw applied at that step; NaN when state is None, :238).
+ * Returns the number of moves made (odometer), or -1 on a reference KeyError, -2 when the
+ * recorded spawn list is exhausted before the game is over.
+ */
+int FN(orc_episode_replay)(int n, REAL *w, REAL alpha, const int32_t *start,
+                           const int32_t *tiles, int n_tiles,
+                           int32_t *moves, REAL *values, REAL *dws,
+                           int32_t *final_row, int64_t *final_score)
+{
+    int32_t row[16], state[16], best_row[16];
+    int64_t score = 0, best_score = 0;
+    int have_state = 0, odo = 0;
+    REAL old_label = 0;
+    int F = orc_num_feat(n);
+    memcpy(row, start, sizeof row);
+    while (!orc_game_over(row)) {
+        REAL best_value;
+        int action = FN(best_move)(n, w, row, score, best_row, &best_score, &best_value, NULL);
+        if (action < 0) return -1;
+        REAL dw = NAN;
+        if (have_state) {                                            /* :238-241 */
+            dw = ((REAL)(best_score - score) + best_value - old_label) * alpha / (REAL)F;
+            FN(orc_update)(n, w, state, dw);
+        }
+        memcpy(row, best_row, sizeof row);                           /* :242 */
+        score = best_score;
+        moves[odo] = action; values[odo] = best_value; dws[odo] = dw;
+        memcpy(state, row, sizeof row);                              /* :245 */
+        old_label = best_value; have_state = 1;
+        if (odo >= n_tiles) return -2;
+        row[tiles[3 * odo + 1] * 4 + tiles[3 * odo + 2]] = tiles[3 * odo];   /* :246 */
+        odo++;
+    }
+    moves[odo] = -1;                                                 /* :247 */
+    {
+        REAL dw = -old_label * alpha / (REAL)F;                      /* :248-249 */
+        if (have_state) FN(orc_update)(n, w, state, dw);
+        values[odo] = 0; dws[odo] = dw;
+    }
+    memcpy(final_row, row, sizeof row);
+    *final_score = score;
+    return odo;
+}
+
+/*
+ * game_logic.py:170-183  Game.trial_run at depth 0 (look_forward :215-216 == estimator call),
+ * teacher-forced on the recorded spawns.  Returns odometer; no -1 sentinel (contrast episode).
+ */
+int FN(orc_trial_replay)(int n, const REAL *w, const int32_t *start,
+                         const int32_t *tiles, int n_tiles, int limit_tile, int step_limit,
+                         int32_t *moves, REAL *values, int32_t *final_row, int64_t *final_score)
+{
+    int32_t row[16], best_row[16];
+    int64_t score = 0, best_score = 0;
+    int odo = 0;
+    memcpy(row, start, sizeof row);
+    while (odo < step_limit) {
+        if (orc_game_over(row)) break;
+        if (limit_tile && orc_max_tile(row) >= limit_tile) break;
+        REAL best_value;
+        int action = FN(best_move)(n, w, row, score, best_row, &best_score, &best_value, NULL);
+        if (action < 0) return -1;
+        memcpy(row, best_row, sizeof row);
+        score = best_score;
+        moves[odo] = action; values[odo] = best_value;
+        if (odo >= n_tiles) return -2;
+        row[tiles[3 * odo + 1] * 4 + tiles[3 * odo + 2]] = tiles[3 * odo];
+        odo++;
+    }
+    memcpy(final_row, row, sizeof row);
+    *final_score = score;
+    return odo;
+}
+
+/*
+ * Greedy play of games [first_id, first_id + num) with the counter-based Philox spawn stream
+ * (SPEC in oracle.c: orc_spawn_*).  Same loop as orc_trial_replay.  Games are independent, so
+ * this is the one place the oracle uses all host threads (OpenMP) -- it is the CPU baseline for
+ * the greedy metric.  Per game: final score, moves, max tile, final packed board; total number of
+ * evaluate() calls (valid afterstates) is returned through n_eval.
+ */
+int64_t FN(orc_play_philox)(int n, const REAL *w, uint64_t seed, uint64_t first_id, int64_t num,
+                            int limit_tile, int step_limit, int threads,
+                            int64_t *scores, int32_t *n_moves, int32_t *max_tile,
+                            uint64_t *final_board, int64_t *n_eval)
+{
+    int64_t total_moves = 0, total_eval = 0;
+    int err = 0;
+#ifdef _OPENMP
+    if (threads <= 0) threads = omp_get_max_threads();
+#pragma omp parallel for schedule(dynamic, 4) num_threads(threads) reduction(+ : total_moves, total_eval)
+#endif
+    for (int64_t g = 0; g < num; g++) {
+        int32_t row[16], best_row[16];
+        int64_t score = 0, best_score = 0;
+        int odo = 0, ovf = 0;
+        uint64_t id = first_id + (uint64_t)g;
+        orc_spawn_initial(seed, id, row);
+        while (odo < step_limit) {
+            if (orc_game_over(row)) break;
+            if (limit_tile && orc_max_tile(row) >= limit_tile) break;
+            REAL best_value;
+            int nv = 0;
+            int action = FN(best_move)(n, w, row, score, best_row, &best_score, &best_value, &nv);
+            if (action < 0) { ovf = 1; break; }
+            if (orc_max_tile(best_row) > 15) { ovf = 1; break; }   /* 2^16 escape: flag + stop */
+            total_eval += nv;
+            memcpy(row, best_row, sizeof row);
+            score = best_score;
+            odo++;
+            orc_spawn_move(seed, id, (uint32_t)odo, row);
+        }
+        if (ovf) err = 1;
+        total_moves += odo;
+        if (scores) scores[g] = score;
+        if (n_moves) n_moves[g] = odo;
+        if (max_tile) max_tile[g] = orc_max_tile(row);
+        if (final_board) final_board[g] = orc_pack(row);
+    }
+    if (n_eval) *n_eval = total_eval;
+    (void)err;
+    return total_moves;
+}
+
+/*
+ * Lock-step batched TD(0): B game slots share one weight table (SURVEY 7.2 "B>1 lock-step").
+ * One lock-step = for every slot, in slot order, the body of QAgent.episode's while loop
+ * (r_learning.py:228-246) or, if the slot's game is over, its terminal update (:247-249) followed by
+ * an in-place restart with game id += id_stride.  All slots evaluate with the weights W_t of the
+ * start of the lock-step; their updates are applied after all evaluations:
+ *   segmented == 0 : w[k] += dw one contribution at a time, slot order, reference key order
+ *   segmented == 1 : S[k] = sum of the contributions to key k in slot order (starting from 0),
+ *                    w[k] += S[k]                              (W_{t+1} = W_t + sum of deltas)
+ *   segmented == 2 : as 1, but w[k] += S[k] / G[k] with G[k] = number of DISTINCT slots that
+ *                    contributed to k in this lock-step ("per-key mean over games"; this is what
+ *                    keeps B >> 1 stable at the reference's alpha; G = 1 when B = 1)
+ * With B == 1 and segmented == 0 this is exactly QAgent.episode repeated.
+ * State arrays are in/out so the call can be chained; `init` != 0 starts fresh games with ids
+ * first_id + slot.  Returns the number of TD updates (update() call equivalents) performed.
+ */
+int64_t FN(orc_td_lockstep)(int n, REAL *w, REAL alpha, uint64_t seed, uint64_t first_id,
+                            uint64_t id_stride, int B, int steps, int segmented, int init,
+                            int threads,
+                            uint64_t *board, int64_t *score, int32_t *odo, uint64_t *game_id,
+                            uint64_t *state, REAL *old_label, uint8_t *have_state,
+                            int64_t *fin_count, int64_t *fin_score_sum, int64_t *fin_moves_sum,
+                            int32_t *fin_max_tile_hist /* [17] */, int64_t *n_moves_out)
+{
+    int F = orc_num_feat(n);
+    int64_t n_updates = 0, n_moves = 0;
+    uint64_t *upd_board = (uint64_t *)malloc(sizeof(uint64_t) * B);
+    REAL *upd_dw = (REAL *)malloc(sizeof(REAL) * B);
+    uint8_t *upd_on = (uint8_t *)malloc(B);
+    REAL *delta = NULL;
+    int64_t *touched = NULL;
+    int32_t *gcount = NULL, *last_slot = NULL;
+    if (segmented) {
+        delta = (REAL *)calloc((size_t)orc_num_weights(n), sizeof(REAL));
+        touched = (int64_t *)malloc(sizeof(int64_t) * (size_t)B * 8 * ORC_MAX_FEAT);
+        gcount = (int32_t *)calloc((size_t)orc_num_weights(n), sizeof(int32_t));
+        last_slot = (int32_t *)malloc((size_t)orc_num_weights(n) * sizeof(int32_t));
+        memset(last_slot, 0xff, (size_t)orc_num_weights(n) * sizeof(int32_t));
+    }
+    if (init) {
+        for (int j = 0; j < B; j++) {
+            int32_t row[16];
+            game_id[j] = first_id + (uint64_t)j;
+            orc_spawn_initial(seed, game_id[j], row);
+            board[j] = orc_pack(row);
+            score[j] = 0; odo[j] = 0; state[j] = 0; old_label[j] = 0; have_state[j] = 0;
+        }
+    }
+#ifdef _OPENMP
+    if (threads <= 0) threads = omp_get_max_threads();
+#endif
+    for (int s = 0; s < steps; s++) {
+        /* phase A: every slot evaluates against W_t (read-only -> parallel over slots) */
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) num_threads(threads)
+#endif
+        for (int j = 0; j < B; j++) {
+            int32_t row[16], best_row[16];
+            orc_unpack(board[j], row);
+            upd_on[j] = 0;
+            if (orc_game_over(row)) {
+                if (have_state[j]) {
+                    upd_on[j] = 1; upd_board[j] = state[j];
+                    upd_dw[j] = -old_label[j] * alpha / (REAL)F;
+                }
+                /* bookkeeping for the finished game is done in the serial phase below */
+                upd_on[j] |= 2;
+                continue;
+            }
+            int64_t best_score = 0;
+            REAL best_value;
+            int action = FN(best_move)(n, w, row, score[j], best_row, &best_score, &best_value, NULL);
+            (void)action;
+            if (have_state[j]) {
+                upd_on[j] = 1; upd_board[j] = state[j];
+                upd_dw[j] = ((REAL)(best_score - score[j]) + best_value - old_label[j]) * alpha / (REAL)F;
+            }
+            score[j] = best_score;
+            odo[j] += 1;
+            state[j] = orc_pack(best_row);
+            old_label[j] = best_value;
+            have_state[j] = 1;
+            orc_spawn_move(seed, game_id[j], (uint32_t)odo[j], best_row);
+            board[j] = orc_pack(best_row);
+            upd_on[j] |= 4;
+        }
+        /* serial bookkeeping + phase B: apply updates in slot order */
+        int64_t nt = 0;
+        for (int j = 0; j < B; j++) {
+            if (upd_on[j] & 4) n_moves++;
+            if (upd_on[j] & 2) {
+                int32_t row[16];
+                orc_unpack(board[j], row);
+                if (fin_count) (*fin_count)++;
+                if (fin_score_sum) *fin_score_sum += score[j];
+                if (fin_moves_sum) *fin_moves_sum += odo[j];
+                if (fin_max_tile_hist) fin_max_tile_hist[orc_max_tile(row)]++;
+                game_id[j] += id_stride;
+                orc_spawn_initial(seed, game_id[j], row);
+                board[j] = orc_pack(row);
+                score[j] = 0; odo[j] = 0; state[j] = 0; old_label[j] = 0; have_state[j] = 0;
+            }
+            if (!(upd_on[j] & 1)) continue;
+            int32_t srow[16];
+            orc_unpack(upd_board[j], srow);
+            n_updates++;
+            if (!segmented) {
+                FN(orc_update)(n, w, srow, upd_dw[j]);
+            } else {
+                int64_t keys[8 * ORC_MAX_FEAT];
+                int m = FN(orc_update_keys)(n, srow, keys);
+                for (int q = 0; q < m; q++) {
+                    delta[keys[q]] += upd_dw[j];
+                    if (last_slot[keys[q]] != j) { last_slot[keys[q]] = j; gcount[keys[q]]++; }
+                    touched[nt++] = keys[q];
+                }
+            }
+        }
+        if (segmented) {
+            for (int64_t q = 0; q < nt; q++) {
+                int64_t k = touched[q];
+                if (gcount[k]) {
+                    w[k] += segmented == 2 ? delta[k] / (REAL)gcount[k] : delta[k];
+                    delta[k] = 0; gcount[k] = 0; last_slot[k] = -1;
+                }
+            }
+        }
+    }
+    free(upd_board); free(upd_dw); free(upd_on); free(delta); free(touched); free(gcount); free(last_slot);
+    if (n_moves_out) *n_moves_out = n_moves;
+    return n_updates;
+}
+
+#undef FN
+#undef CAT
+#undef CAT_
