@@ -529,6 +529,15 @@ __device__ __forceinline__ void warp_add_counter(uint64_t *ctr, uint32_t v)
     if ((threadIdx.x & 31) == 0 && v) atomicAdd(reinterpret_cast<unsigned long long *>(ctr), (unsigned long long)v);
 }
 
+__device__ __forceinline__ void log_finished(const b2048_games_t &g, uint64_t id, uint32_t score, uint32_t moves,
+                                             uint32_t max_exp)
+{
+    if (!g.fin_log) return;
+    unsigned long long idx = atomicAdd(reinterpret_cast<unsigned long long *>(g.counters + B2048_CTR_LOG), 1ULL);
+    if (int64_t(idx) < g.fin_cap)
+        reinterpret_cast<uint4 *>(g.fin_log)[idx] = make_uint4(uint32_t(id), score, moves, max_exp);
+}
+
 // One afterstate per lane (lane d of a 4-lane group = direction d), value by n-tuple gather, then a
 // width-4 shuffle argmax with the reference's tie rule (strict '>' scanning d = 0..3: lowest d wins).
 template <int N>
@@ -562,7 +571,7 @@ template <int N>
 __global__ void __launch_bounds__(128)
 greedy_play_kernel(const float *__restrict__ w, const uint32_t *__restrict__ lut, b2048_games_t g, int max_steps,
                    int limit_tile, int step_limit, b2048_replay_t rp, int has_replay, int8_t *__restrict__ trace_dir,
-                   float *__restrict__ trace_value, int64_t trace_len)
+                   float *__restrict__ trace_value, uint16_t *__restrict__ trace_spawn, int64_t trace_len)
 {
     const int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
     const int64_t slot = t >> 2;
@@ -586,6 +595,7 @@ greedy_play_kernel(const float *__restrict__ w, const uint32_t *__restrict__ lut
                 if (d == 0) {
                     c_fin++; c_score += score; c_msum += odo;
                     atomicAdd(g.tile_hist + max_tile(board), 1u);
+                    log_finished(g, id, score, odo, max_tile(board));
                 }
             }
         }
@@ -601,7 +611,11 @@ greedy_play_kernel(const float *__restrict__ w, const uint32_t *__restrict__ lut
             if (bf & 2u) {                                          // 2^16 escape: flag + stop
                 flags |= B2048_F_DONE | B2048_F_OVERFLOW;
                 run = false;
-                if (d == 0) { c_fin++; c_score += score; c_msum += odo; c_ovf++; atomicAdd(g.tile_hist + 16, 1u); }
+                if (d == 0) {
+                    c_fin++; c_score += score; c_msum += odo; c_ovf++;
+                    atomicAdd(g.tile_hist + 16, 1u);
+                    log_finished(g, id, score, odo, 16u);
+                }
             } else {
                 if (d == 0) {
                     c_moves++; c_evals += nv;
@@ -610,16 +624,20 @@ greedy_play_kernel(const float *__restrict__ w, const uint32_t *__restrict__ lut
                 }
                 board = ba;
                 score += bg;
+                uint32_t sp;
                 if (has_replay) {
                     uint32_t tl = __ldg(rp.tile + slot * rp.len + odo);
-                    int sh = 4 * (15 - int(__ldg(rp.pos + slot * rp.len + odo) & 15));
+                    uint32_t ps = __ldg(rp.pos + slot * rp.len + odo) & 15u;
+                    int sh = 4 * (15 - int(ps));
                     board = (board & ~(0xFULL << sh)) | (uint64_t(tl & 15u) << sh);
+                    sp = (tl << 8) | ps;
                     odo++;
                 } else {
                     odo++;
                     Philox4 r = spawn_words(g.seed, id, odo, 0u);
-                    spawn_apply(board, r.x, r.y);
+                    sp = spawn_apply(board, r.x, r.y);
                 }
+                if (d == 0 && trace_spawn && int64_t(odo) <= trace_len) trace_spawn[slot * trace_len + odo - 1] = uint16_t(sp);
             }
         }
     }
@@ -644,7 +662,7 @@ __global__ void __launch_bounds__(128)
 td_phase_a_kernel(const float *__restrict__ w, const uint32_t *__restrict__ lut, b2048_games_t g, float alpha,
                   uint64_t *__restrict__ upd_board, float *__restrict__ upd_dw, b2048_replay_t rp, int has_replay,
                   int8_t *__restrict__ trace_dir, float *__restrict__ trace_value, float *__restrict__ trace_dw,
-                  int64_t trace_len)
+                  uint16_t *__restrict__ trace_spawn, int64_t trace_len)
 {
     constexpr int F = num_feat(N);
     const int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
@@ -683,6 +701,7 @@ td_phase_a_kernel(const float *__restrict__ w, const uint32_t *__restrict__ lut,
                 c_fin++; c_score += score; c_msum += odo;
                 if (!over) c_ovf++;
                 atomicAdd(g.tile_hist + (over ? max_tile(board) : 16), 1u);
+                log_finished(g, id, score, odo, over ? uint32_t(max_tile(board)) : 16u);
                 if (trace_dir && int64_t(odo) < trace_len) {
                     trace_dir[slot * trace_len + odo] = -1;          // :247 sentinel
                     if (trace_value) trace_value[slot * trace_len + odo] = 0.0f;
@@ -717,16 +736,20 @@ td_phase_a_kernel(const float *__restrict__ w, const uint32_t *__restrict__ lut,
             state = ba;
             old_label = bv;
             flags |= B2048_F_HAVE_STATE;
+            uint32_t sp;
             if (has_replay) {                                        // :246 new_tile
                 uint32_t tl = __ldg(rp.tile + slot * rp.len + odo);
-                int sh = 4 * (15 - int(__ldg(rp.pos + slot * rp.len + odo) & 15));
+                uint32_t ps = __ldg(rp.pos + slot * rp.len + odo) & 15u;
+                int sh = 4 * (15 - int(ps));
                 board = (board & ~(0xFULL << sh)) | (uint64_t(tl & 15u) << sh);
+                sp = (tl << 8) | ps;
                 odo++;
             } else {
                 odo++;
                 Philox4 r = spawn_words(g.seed, id, odo, 0u);
-                spawn_apply(board, r.x, r.y);
+                sp = spawn_apply(board, r.x, r.y);
             }
+            if (d == 0 && trace_spawn && int64_t(odo) <= trace_len) trace_spawn[slot * trace_len + odo - 1] = uint16_t(sp);
         }
         if (d == 0 && !isnan(dw)) c_upd++;
     }
@@ -1042,7 +1065,7 @@ int b2048_games_init(const b2048_games_t *g, uint64_t first_id, int reset_counte
 
 int b2048_greedy_play(int n, const float *weights, const uint32_t *lut, const b2048_games_t *g, int max_steps,
                       int limit_tile, int step_limit, const b2048_replay_t *replay, int8_t *trace_dir,
-                      float *trace_value, int64_t trace_len, b2048_stream_t stream)
+                      float *trace_value, uint16_t *trace_spawn, int64_t trace_len, b2048_stream_t stream)
 {
     if (!games_ok(g) || num_feat(n) < 0 || !weights || !lut || max_steps < 0) return B2048_EINVAL;
     if (replay && (!replay->tile || !replay->pos || replay->len < 0)) return B2048_EINVAL;
@@ -1053,25 +1076,35 @@ int b2048_greedy_play(int n, const float *weights, const uint32_t *lut, const b2
     unsigned grid = unsigned(cdiv(g->B * 4, 128));
     DISPATCH_N(n, greedy_play_kernel<N><<<grid, 128, 0, S(stream)>>>(weights, lut, *g, max_steps, limit_tile, step_limit,
                                                                      rp, replay ? 1 : 0, trace_dir, trace_value,
-                                                                     trace_len));
+                                                                     trace_spawn, trace_len));
+    return launch_status();
+}
+
+int b2048_td_phase_a(int n, const float *weights, const uint32_t *lut, const b2048_games_t *g, float alpha,
+                     uint64_t *upd_board, float *upd_dw, const b2048_replay_t *replay, int8_t *trace_dir,
+                     float *trace_value, float *trace_dw, uint16_t *trace_spawn, int64_t trace_len,
+                     b2048_stream_t stream)
+{
+    if (!games_ok(g) || num_feat(n) < 0 || !weights || !lut || !upd_board || !upd_dw) return B2048_EINVAL;
+    if (replay && (!replay->tile || !replay->pos || replay->len < 0)) return B2048_EINVAL;
+    if (g->B == 0) return 0;
+    b2048_replay_t rp = replay ? *replay : b2048_replay_t{nullptr, nullptr, 0};
+    unsigned grid = unsigned(cdiv(g->B * 4, 128));
+    DISPATCH_N(n, td_phase_a_kernel<N><<<grid, 128, 0, S(stream)>>>(weights, lut, *g, alpha, upd_board, upd_dw, rp,
+                                                                   replay ? 1 : 0, trace_dir, trace_value, trace_dw,
+                                                                   trace_spawn, trace_len));
     return launch_status();
 }
 
 int b2048_td_step(int n, float *weights, float *delta, const uint32_t *lut, const b2048_games_t *g, float alpha,
                   int mode, uint64_t *upd_board, float *upd_dw, void *work, size_t work_bytes,
                   const b2048_replay_t *replay, int8_t *trace_dir, float *trace_value, float *trace_dw,
-                  int64_t trace_len, b2048_stream_t stream)
+                  uint16_t *trace_spawn, int64_t trace_len, b2048_stream_t stream)
 {
-    if (!games_ok(g) || num_feat(n) < 0 || !weights || !lut || !upd_board || !upd_dw || (mode & ~3)) return B2048_EINVAL;
-    if (replay && (!replay->tile || !replay->pos || replay->len < 0)) return B2048_EINVAL;
-    if (g->B == 0) return 0;
-    b2048_replay_t rp = replay ? *replay : b2048_replay_t{nullptr, nullptr, 0};
-    unsigned grid = unsigned(cdiv(g->B * 4, 128));
-    DISPATCH_N(n, td_phase_a_kernel<N><<<grid, 128, 0, S(stream)>>>(weights, lut, *g, alpha, upd_board, upd_dw, rp,
-                                                                    replay ? 1 : 0, trace_dir, trace_value, trace_dw,
-                                                                    trace_len));
-    int rc = launch_status();
-    if (rc) return rc;
+    if (mode & ~3) return B2048_EINVAL;
+    int rc = b2048_td_phase_a(n, weights, lut, g, alpha, upd_board, upd_dw, replay, trace_dir, trace_value, trace_dw,
+                              trace_spawn, trace_len, stream);
+    if (rc || g->B == 0) return rc;
     return td_update_impl(n, weights, delta, upd_board, upd_dw, g->B, mode, work, work_bytes, S(stream));
 }
 
@@ -1082,7 +1115,7 @@ int b2048_td_run(int n, float *weights, float *delta, const uint32_t *lut, const
     if (steps < 0) return B2048_EINVAL;
     for (int s = 0; s < steps; s++) {
         int rc = b2048_td_step(n, weights, delta, lut, g, alpha, mode, upd_board, upd_dw, work, work_bytes, nullptr,
-                               nullptr, nullptr, nullptr, 0, stream);
+                               nullptr, nullptr, nullptr, nullptr, 0, stream);
         if (rc) return rc;
     }
     return 0;

@@ -1,0 +1,390 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native 2048 / n-tuple hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload td|greedy|sweep]
+
+Workload `td` (default) is BASELINE.json configs[1]: Q_agent n=4 TD(0) training, 4,096 parallel seeded games
+per GPU (weak scaling), per-key-mean lock-step rule, atomic update mode; one bench "step" = `--lock-steps`
+lock-steps of all games.  metric = TD updates/s (one update = one QAgent.update() equivalent = 8*F weight
+RMWs).  One JSON line on stdout (rank 0); see DESIGN.md "Measurement" for every field.
+
+--impl reference times the CPU restatement of the reference algorithm (oracle/, C + OpenMP, all host
+threads) on a bounded sample of the same workload; the Python reference itself cannot travel to the GPU box.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+F_OF_N = {2: 24, 3: 52, 4: 17, 5: 21, 6: 33}
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=8)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--workload", default="td", choices=["td", "greedy", "sweep"])
+    p.add_argument("--n", type=int, default=4)
+    p.add_argument("--games", type=int, default=4096, help="game slots per GPU")
+    p.add_argument("--lock-steps", type=int, default=256, help="lock-steps per bench step (td)")
+    p.add_argument("--mode", default="atomic", choices=["atomic", "deterministic"])
+    p.add_argument("--rule", default="mean", choices=["mean", "sum"])
+    p.add_argument("--alpha", type=float, default=0.25)
+    p.add_argument("--sync-every", type=int, default=64, help="lock-steps between weight-delta allreduces (N>1)")
+    p.add_argument("--boards", type=int, default=1 << 24, help="boards per GPU (sweep)")
+    p.add_argument("--no-extras", action="store_true")
+    p.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
+    return p.parse_args()
+
+
+# --------------------------------------------------------------------------------------------- helpers
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def seeded_weights(n, seed=0):
+    """the reference's init (np.random.random/100, r_learning.py:136-149) from a seeded legacy stream, float32"""
+    sig = {2: (24,), 3: (52,), 4: (17,), 5: (17, 4), 6: (17, 4, 12)}[n]
+    size = {2: (256,), 3: (4096,), 4: (65536,), 5: (65536, 1048576), 6: (65536, 1048576, 14 ** 6)}[n]
+    rs = np.random.RandomState(seed)
+    return np.concatenate([(rs.random_sample((d, s)) / 100).astype(np.float32).reshape(-1) for d, s in zip(sig, size)])
+
+
+def mode_bits(cabi, args):
+    return (cabi.UPD_DETERMINISTIC if args.mode == "deterministic" else cabi.UPD_ATOMIC) | \
+           (cabi.UPD_MEAN if args.rule == "mean" else cabi.UPD_SUM)
+
+
+def bytes_per_update(n, evals_per_move):
+    F = F_OF_N[n]
+    return 16 + 4 * F * evals_per_move + 64 * F          # board in/out + gathers + 8F RMWs x (4+4) B
+
+
+# --------------------------------------------------------------------------------------------- reference arm
+def cpu_td_sample(args, seconds, threads=0):
+    """oracle lock-step TD (float32, per-key-mean rule == the GPU's semantics) on the host cores"""
+    from oracle import oracle as orc
+    orc.build()
+    threads = threads or orc.max_threads()
+    rule = 2 if args.rule == "mean" else 1
+    w = seeded_weights(args.n)
+    ls = orc.LockStep(args.n, w, args.alpha, 0, args.games, segmented=rule, threads=threads)
+    ls.run(2)                                            # touch memory
+    u0, t0, steps = ls.n_updates, time.perf_counter(), 0
+    chunk = 4
+    while True:
+        ls.run(chunk)
+        steps += chunk
+        dt = time.perf_counter() - t0
+        if dt >= seconds:
+            break
+        chunk = max(1, min(64, int(chunk * seconds / max(dt, 1e-3) / 4)))
+    return (ls.n_updates - u0) / dt, threads, f"{steps} lock-steps of {args.games} games, n={args.n} ({dt:.1f} s)"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    orc.build()
+    threads = orc.max_threads()
+    rule = 2 if args.rule == "mean" else 1
+    w = seeded_weights(args.n)
+    ls = orc.LockStep(args.n, w, args.alpha, 0, args.games, segmented=rule, threads=threads)
+    per_step = max(1, min(args.lock_steps, 8))           # bounded sample of the GPU step
+    for _ in range(args.warmup):
+        ls.run(per_step)
+    u0, t0 = ls.n_updates, time.perf_counter()
+    for _ in range(args.steps):
+        ls.run(per_step)
+    dt = time.perf_counter() - t0
+    val = (ls.n_updates - u0) / dt
+    sample = f"{per_step} lock-steps of {args.games} games per step (GPU step = {args.lock_steps})"
+    line = {"impl": "reference", "metric": "td_updates_per_sec", "value": val, "unit": "updates/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args),
+            "cpu_baseline": {"value": val, "unit": "updates/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    return {"workload": f"BASELINE configs[1]: Q_agent n={args.n} TD(0), {args.games} parallel seeded games per GPU, "
+                        f"{args.lock_steps} lock-steps per step, rule={args.rule}, update mode={args.mode}",
+            "n": args.n, "games_per_gpu": args.games, "lock_steps_per_step": args.lock_steps, "alpha": args.alpha,
+            "update_mode": args.mode, "update_rule": args.rule, "sync_every": args.sync_every,
+            "l2": "weight tables (4.46 MB at n=4) are L2-resident by construction; a 256 MiB buffer is written "
+                  "between timed steps to flush L2"}
+
+
+# --------------------------------------------------------------------------------------------- GPU arm
+def run_td(args):
+    import torch
+    import torch.distributed as dist
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    importlib.import_module("2048_b200")
+    from game2048 import cabi, engine
+    ctx = engine.Context.get()
+    n, B, S = args.n, args.games, args.lock_steps
+    mode = mode_bits(cabi, args)
+    w_host = torch.from_numpy(seeded_weights(n)).pin_memory()
+    wd = w_host.to(ctx.device)
+    games = engine.GameBatch(B, seed=0, id_stride=B * world, ctx=ctx).init(first_id=rank * B)
+    delta = ctx.zeros(wd.numel(), torch.float32) if world > 1 else None
+    w_sync = wd.clone() if world > 1 else None
+    dsum = ctx.zeros(wd.numel(), torch.float32) if world > 1 else None
+    tr = engine.TDTrainer(ctx, n, wd, games, args.alpha, mode, delta=delta)
+    flush = ctx.zeros(64 << 20, torch.int32)                     # 256 MiB > 126 MB L2
+    launches_per_lockstep = {0: 2, 2: 3}.get(mode, None)
+
+    def step():
+        if world == 1:
+            tr.run(S)
+            return
+        done = 0
+        while done < S:
+            k = min(args.sync_every, S - done)
+            tr.run(k)
+            dsum.copy_(delta)
+            dist.all_reduce(dsum, op=dist.ReduceOp.AVG)          # NCCL over NVLink: model averaging of the deltas
+            check = ctx.lib.b2048_delta_apply(engine.dptr(wd), engine.dptr(w_sync), engine.dptr(delta),
+                                              engine.dptr(dsum), wd.numel(), engine.cur_stream())
+            cabi.check(check, "delta_apply")
+            done += k
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    c0 = games.read_counters()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for a, b in ev:
+        flush.fill_(1)
+        a.record()
+        step()
+        b.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    c1 = games.read_counters()
+    upd = c1["updates"] - c0["updates"]
+    mv = c1["moves"] - c0["moves"]
+    evals = c1["evals"] - c0["evals"]
+    t = torch.tensor([ms, float(upd), float(mv), float(evals)], dtype=torch.float64, device=ctx.device)
+    if world > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms, upd, mv, evals = float(tmax[0]), float(tsum[1]), float(tsum[2]), float(tsum[3])
+    value = upd / (ms * 1e-3)
+
+    # ---- e2e: the same step through host buffers: weights H2D (pinned) -> S lock-steps -> weights + counters D2H
+    e2e_ms, e2e_upd = 0.0, 0
+    h2d = d2h = 0
+    if world == 1:
+        for i in range(args.steps + 1):
+            cA = games.read_counters()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            a.record()
+            wd.copy_(w_host, non_blocking=True)
+            tr.run(S)
+            w_host.copy_(wd, non_blocking=True)
+            cnt = games.counters.cpu()                           # D2H read of the step's result
+            b.record()
+            torch.cuda.synchronize()
+            if i:                                                # first pass = warm-up
+                e2e_ms += a.elapsed_time(b)
+                e2e_upd += int(cnt[cabi.CTR_UPDATES]) - cA["updates"]
+        h2d, d2h = wd.numel() * 4, wd.numel() * 4 + cabi.CTR_COUNT * 8
+    else:
+        e2e_ms, e2e_upd = ms, upd                                # multi-GPU: weights stay resident between syncs
+    e2e = {"value": e2e_upd / (e2e_ms * 1e-3) if e2e_ms else None, "unit": "updates/s",
+           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
+
+    # ---- roofline of the dominant kernel group: phase A (gather) and phase B (scatter) timed separately
+    roof = None
+    if rank == 0:
+        probe = 64
+        ea = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+              for _ in range(probe)]
+        cA = games.read_counters()
+        for x, y, z in ea:
+            x.record(); tr.phase_a(); y.record(); tr.phase_b(); z.record()
+        torch.cuda.synchronize()
+        cB = games.read_counters()
+        ta = sum(x.elapsed_time(y) for x, y, z in ea) / probe * 1e-3
+        tb = sum(y.elapsed_time(z) for x, y, z in ea) / probe * 1e-3
+        u = (cB["updates"] - cA["updates"]) / probe
+        e_per_move = (cB["evals"] - cA["evals"]) / max(cB["moves"] - cA["moves"], 1)
+        F = F_OF_N[n]
+        peak, how = peaks()
+        bytes_a, bytes_b = u * (16 + 4 * F * e_per_move), u * 64 * F
+        dom = "td_update (phase B scatter: 8F RMW per update)" if tb >= ta else "td_phase_a (gather + argmax + spawn)"
+        ach = (bytes_b / tb if tb >= ta else bytes_a / ta) / 1e9
+        roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": None, "peak_source": how, "phase_a_us": ta * 1e6, "phase_b_us": tb * 1e6,
+                "updates_per_launch": u, "evals_per_move": e_per_move,
+                "whole_step_achieved_GBps": value / world * bytes_per_update(n, e_per_move) / 1e9,
+                "note": "tables are L2-resident (4.46 MB): the HBM copy peak is the judged denominator, L2 the physical one"}
+
+    extras = {}
+    if rank == 0 and world == 1 and not args.no_extras:
+        extras = td_extras(args, ctx, engine, cabi, wd)
+    cpu = None
+    if rank == 0 and world == 1:
+        v, cores, sample = cpu_td_sample(args, args.cpu_seconds)
+        cpu = {"value": v, "unit": "updates/s", "cores": cores, "kind": "port", "sample": sample}
+    if rank == 0:
+        line = {"metric": "td_updates_per_sec", "value": value, "unit": "updates/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": workload_config(args), "moves_per_sec": mv / (ms * 1e-3), "clocks": clocks, "e2e": e2e,
+                "gpu_launches": (launches_per_lockstep or 0) * S * args.steps if launches_per_lockstep else
+                S * args.steps * (3 + 3 * 3),
+                "roofline": roof, "cpu_baseline": cpu, "extras": extras}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def td_extras(args, ctx, engine, cabi, wd):
+    """secondary numbers on the same box: deterministic-mode updates/s, greedy moves/s, board sweep"""
+    import torch
+    out = {}
+    n, B = args.n, args.games
+
+    def timed(fn, reps):
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) * 1e-3
+
+    for name, mode in (("deterministic_mean", cabi.UPD_DETERMINISTIC | cabi.UPD_MEAN),
+                       ("atomic_sum", cabi.UPD_ATOMIC | cabi.UPD_SUM)):
+        w2 = wd.clone()
+        g2 = engine.GameBatch(B, seed=1, ctx=ctx).init()
+        alpha = args.alpha if mode & cabi.UPD_MEAN else args.alpha / B
+        t2 = engine.TDTrainer(ctx, n, w2, g2, alpha, mode)
+        t2.run(64)
+        c0 = g2.read_counters()
+        dt = timed(lambda: t2.run(64), 2)
+        c1 = g2.read_counters()
+        out[f"td_updates_per_sec_{name}"] = (c1["updates"] - c0["updates"]) / dt
+    # greedy play, BASELINE configs[0] shape: 1,000 seeded games to completion from the trained-so-far weights
+    g3 = engine.GameBatch(1000, seed=2, ctx=ctx).init()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    engine.greedy_play(ctx, n, wd, g3)
+    b.record()
+    torch.cuda.synchronize()
+    c = g3.read_counters()
+    out["greedy_1000_games_moves_per_sec"] = c["moves"] / (a.elapsed_time(b) * 1e-3)
+    out["greedy_1000_games_avg_score"] = c["score_sum"] / max(c["finished"], 1)
+    # config 5 sweep: 16M boards
+    m = args.boards
+    gen = torch.Generator(device=ctx.device).manual_seed(0)      # cell iid: empty p=0.3 else exponent 1..11
+    cells = torch.randint(1, 12, (m, 16), dtype=torch.int32, device=ctx.device, generator=gen)
+    cells.mul_((torch.rand((m, 16), device=ctx.device, generator=gen) >= 0.3).to(torch.int32))
+    boards = ctx.pack(cells)
+    del cells
+    bufs = ctx.sweep(boards, seed=0)
+    dt = timed(lambda: ctx.sweep(boards, seed=0, out=bufs), 3) / 3
+    out["sweep_boards_per_sec"] = m / dt
+    out["sweep_GBps_algorithmic"] = m * 89 / dt / 1e9
+    return out
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    if args.workload != "td":
+        raise SystemExit("only --workload td is wired as a bench line in this round; greedy and sweep are reported in extras")
+    run_td(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -143,6 +143,9 @@ typedef struct b2048_games {
     uint32_t *tile_hist;  /* [17] finished games by max exponent */
     uint64_t seed;        /* Philox key */
     uint64_t id_stride;   /* TD in-place restart: game_id += id_stride (total slots over all ranks) */
+    uint32_t *fin_log;    /* [fin_cap,4] (game id low 32 bits, score, moves, max exponent) of finished
+                             games in completion order; head = counters[B2048_CTR_LOG]; may be NULL */
+    int64_t fin_cap;      /* records that fit; later finishes are counted but not stored */
 } b2048_games_t;
 
 #define B2048_F_HAVE_STATE 1u /* TD: state/old_label valid */
@@ -158,7 +161,8 @@ enum {
     B2048_CTR_MOVES_SUM = 5,
     B2048_CTR_OVERFLOW = 6,
     B2048_CTR_ACTIVE = 7,   /* greedy_play: slots still playing after the call (overwritten) */
-    B2048_CTR_COUNT = 8
+    B2048_CTR_LOG = 8,      /* finished-game records appended to fin_log (host may reset to 0) */
+    B2048_CTR_COUNT = 16
 };
 
 /* Fresh games in every slot: ids first_id + i, Game.__init__ spawns, zero score/moves/flags;
@@ -170,7 +174,8 @@ int b2048_games_init(const b2048_games_t *g, uint64_t first_id, int reset_counte
  * limit_tile as in trial_run (exponent; 0 = none); step_limit = total odometer cap (100000 there).
  * replay == NULL: Philox spawns.  Otherwise replay mode: tile/pos are [B, replay_len] recorded
  * spawns (tile 0 = exhausted -> slot stops, stays not DONE), indexed by the slot's odometer.
- * trace_dir/trace_value (may be NULL): [B, trace_len] chosen direction / its value per move. */
+ * trace_dir / trace_value / trace_spawn (each may be NULL): [B, trace_len] per move: chosen direction,
+ * its value, and the spawn that followed ((tile << 8) | flat cell) -- Game.moves / Game.tiles. */
 typedef struct b2048_replay {
     const uint8_t *tile;  /* [B, len] */
     const uint8_t *pos;   /* [B, len] flat cell 4r+c */
@@ -178,7 +183,7 @@ typedef struct b2048_replay {
 } b2048_replay_t;
 int b2048_greedy_play(int n, const float *weights, const uint32_t *lut, const b2048_games_t *g, int max_steps,
                       int limit_tile, int step_limit, const b2048_replay_t *replay, int8_t *trace_dir,
-                      float *trace_value, int64_t trace_len, b2048_stream_t stream);
+                      float *trace_value, uint16_t *trace_spawn, int64_t trace_len, b2048_stream_t stream);
 
 /* One lock-step of QAgent.episode (r_learning.py:224-252) for all B slots, two launches:
  *   phase A (every slot, weights W_t read-only): game over -> terminal dw = -old_label*alpha/F
@@ -194,7 +199,13 @@ int b2048_greedy_play(int n, const float *weights, const uint32_t *lut, const b2
 int b2048_td_step(int n, float *weights, float *delta, const uint32_t *lut, const b2048_games_t *g, float alpha,
                   int mode, uint64_t *upd_board, float *upd_dw, void *work, size_t work_bytes,
                   const b2048_replay_t *replay, int8_t *trace_dir, float *trace_value, float *trace_dw,
-                  int64_t trace_len, b2048_stream_t stream);
+                  uint16_t *trace_spawn, int64_t trace_len, b2048_stream_t stream);
+/* phase A alone (one launch); b2048_td_step == b2048_td_phase_a + b2048_td_update(upd_board, upd_dw, B).
+ * Exposed so that callers can time or overlap the gather and the scatter halves separately. */
+int b2048_td_phase_a(int n, const float *weights, const uint32_t *lut, const b2048_games_t *g, float alpha,
+                     uint64_t *upd_board, float *upd_dw, const b2048_replay_t *replay, int8_t *trace_dir,
+                     float *trace_value, float *trace_dw, uint16_t *trace_spawn, int64_t trace_len,
+                     b2048_stream_t stream);
 /* `steps` lock-steps enqueued back to back (no host work in between). */
 int b2048_td_run(int n, float *weights, float *delta, const uint32_t *lut, const b2048_games_t *g, float alpha,
                  int mode, int steps, uint64_t *upd_board, float *upd_dw, void *work, size_t work_bytes,

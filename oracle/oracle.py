@@ -79,6 +79,9 @@ def _declare(L):
         f.restype = None
         f = getattr(L, "orc_update_keys_" + suf)
         f.argtypes = [C.c_int, i32p, i64p]
+        f = getattr(L, "orc_update_batch_" + suf)
+        f.argtypes = [C.c_int, rp, u64p, rp, C.c_int64, C.c_int]
+        f.restype = C.c_int64
         f = getattr(L, "orc_episode_replay_" + suf)
         f.argtypes = [C.c_int, rp, rt, i32p, i32p, C.c_int, i32p, rp, rp, i32p, i64p]
         f = getattr(L, "orc_trial_replay_" + suf)
@@ -214,6 +217,14 @@ def update_keys(n, row):
     keys = np.zeros(8 * NUM_FEAT[n], np.int64)
     m = lib().orc_update_keys_f64(n, _p(r, C.c_int32), _p(keys, C.c_int64))
     return keys[:m]
+
+
+def update_batch(n, w, boards, dw, rule):
+    """b2048_td_update restated: rule 0 sequential, 1 per-key sum then add, 2 per-key mean over entries."""
+    suf, ct = _real(w.dtype)
+    b = np.ascontiguousarray(boards, dtype=np.uint64)
+    d = np.ascontiguousarray(dw, dtype=w.dtype)
+    return getattr(lib(), "orc_update_batch_" + suf)(n, _p(w, ct), _p(b, C.c_uint64), _p(d, ct), len(b), rule)
 
 
 def _tiles_array(tiles):

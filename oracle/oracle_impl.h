@@ -219,6 +219,72 @@ int64_t FN(orc_play_philox)(int n, const REAL *w, uint64_t seed, uint64_t first_
 }
 
 /*
+ * update() for m (board, dw) entries sharing one table set -- the restatement b2048_td_update is
+ * checked against.  Entries with NaN dw are skipped.  rule:
+ *   0 : w[k] += dw one contribution at a time, entry order, reference key order (QAgent.update x m)
+ *   1 : S[k] = sequential sum (from 0) of the contributions to k in entry order;  w[k] += S[k]
+ *   2 : as 1 but w[k] += S[k] / G[k], G[k] = number of distinct entries contributing to k
+ * scratch: NULL, or {delta[num_weights] zeros, gcount[num_weights] zeros, last[num_weights] = -1,
+ * touched[m*8*F]} kept clean across calls (used by orc_td_lockstep to avoid reallocating).
+ */
+typedef struct { REAL *delta; int32_t *gcount; int32_t *last; int64_t *touched; } FN(orc_scratch);
+
+static void FN(scratch_alloc)(FN(orc_scratch) *sc, int n, int64_t m)
+{
+    size_t nw = (size_t)orc_num_weights(n);
+    sc->delta = (REAL *)calloc(nw, sizeof(REAL));
+    sc->gcount = (int32_t *)calloc(nw, sizeof(int32_t));
+    sc->last = (int32_t *)malloc(nw * sizeof(int32_t));
+    memset(sc->last, 0xff, nw * sizeof(int32_t));
+    sc->touched = (int64_t *)malloc(sizeof(int64_t) * (size_t)(m > 0 ? m : 1) * 8 * ORC_MAX_FEAT);
+}
+
+static void FN(scratch_free)(FN(orc_scratch) *sc)
+{
+    free(sc->delta); free(sc->gcount); free(sc->last); free(sc->touched);
+}
+
+static int64_t FN(update_batch_impl)(int n, REAL *w, const uint64_t *boards, const REAL *dw, int64_t m, int rule,
+                                     FN(orc_scratch) *sc)
+{
+    int64_t n_upd = 0, nt = 0;
+    for (int64_t j = 0; j < m; j++) {
+        if (dw[j] != dw[j]) continue;                 /* NaN = no update */
+        int32_t row[16];
+        orc_unpack(boards[j], row);
+        n_upd++;
+        if (rule == 0) {
+            FN(orc_update)(n, w, row, dw[j]);
+        } else {
+            int64_t keys[8 * ORC_MAX_FEAT];
+            int nk = FN(orc_update_keys)(n, row, keys);
+            for (int q = 0; q < nk; q++) {
+                sc->delta[keys[q]] += dw[j];
+                if (sc->last[keys[q]] != (int32_t)j) { sc->last[keys[q]] = (int32_t)j; sc->gcount[keys[q]]++; }
+                sc->touched[nt++] = keys[q];
+            }
+        }
+    }
+    for (int64_t q = 0; q < nt; q++) {
+        int64_t k = sc->touched[q];
+        if (sc->gcount[k]) {
+            w[k] += rule == 2 ? sc->delta[k] / (REAL)sc->gcount[k] : sc->delta[k];
+            sc->delta[k] = 0; sc->gcount[k] = 0; sc->last[k] = -1;
+        }
+    }
+    return n_upd;
+}
+
+int64_t FN(orc_update_batch)(int n, REAL *w, const uint64_t *boards, const REAL *dw, int64_t m, int rule)
+{
+    FN(orc_scratch) sc = {0};
+    if (rule) FN(scratch_alloc)(&sc, n, m);
+    int64_t r = FN(update_batch_impl)(n, w, boards, dw, m, rule, &sc);
+    if (rule) FN(scratch_free)(&sc);
+    return r;
+}
+
+/*
  * Lock-step batched TD(0): B game slots share one weight table (SURVEY 7.2 "B>1 lock-step").
  * One lock-step = for every slot, in slot order, the body of QAgent.episode's while loop
  * (r_learning.py:228-246) or, if the slot's game is over, its terminal update (:247-249) followed by
@@ -247,16 +313,8 @@ int64_t FN(orc_td_lockstep)(int n, REAL *w, REAL alpha, uint64_t seed, uint64_t 
     uint64_t *upd_board = (uint64_t *)malloc(sizeof(uint64_t) * B);
     REAL *upd_dw = (REAL *)malloc(sizeof(REAL) * B);
     uint8_t *upd_on = (uint8_t *)malloc(B);
-    REAL *delta = NULL;
-    int64_t *touched = NULL;
-    int32_t *gcount = NULL, *last_slot = NULL;
-    if (segmented) {
-        delta = (REAL *)calloc((size_t)orc_num_weights(n), sizeof(REAL));
-        touched = (int64_t *)malloc(sizeof(int64_t) * (size_t)B * 8 * ORC_MAX_FEAT);
-        gcount = (int32_t *)calloc((size_t)orc_num_weights(n), sizeof(int32_t));
-        last_slot = (int32_t *)malloc((size_t)orc_num_weights(n) * sizeof(int32_t));
-        memset(last_slot, 0xff, (size_t)orc_num_weights(n) * sizeof(int32_t));
-    }
+    FN(orc_scratch) sc = {0};
+    if (segmented) FN(scratch_alloc)(&sc, n, B);
     if (init) {
         for (int j = 0; j < B; j++) {
             int32_t row[16];
@@ -304,8 +362,7 @@ int64_t FN(orc_td_lockstep)(int n, REAL *w, REAL alpha, uint64_t seed, uint64_t 
             board[j] = orc_pack(best_row);
             upd_on[j] |= 4;
         }
-        /* serial bookkeeping + phase B: apply updates in slot order */
-        int64_t nt = 0;
+        /* serial bookkeeping (slot order), then phase B = one batch update over the B slots */
         for (int j = 0; j < B; j++) {
             if (upd_on[j] & 4) n_moves++;
             if (upd_on[j] & 2) {
@@ -320,33 +377,12 @@ int64_t FN(orc_td_lockstep)(int n, REAL *w, REAL alpha, uint64_t seed, uint64_t 
                 board[j] = orc_pack(row);
                 score[j] = 0; odo[j] = 0; state[j] = 0; old_label[j] = 0; have_state[j] = 0;
             }
-            if (!(upd_on[j] & 1)) continue;
-            int32_t srow[16];
-            orc_unpack(upd_board[j], srow);
-            n_updates++;
-            if (!segmented) {
-                FN(orc_update)(n, w, srow, upd_dw[j]);
-            } else {
-                int64_t keys[8 * ORC_MAX_FEAT];
-                int m = FN(orc_update_keys)(n, srow, keys);
-                for (int q = 0; q < m; q++) {
-                    delta[keys[q]] += upd_dw[j];
-                    if (last_slot[keys[q]] != j) { last_slot[keys[q]] = j; gcount[keys[q]]++; }
-                    touched[nt++] = keys[q];
-                }
-            }
+            if (!(upd_on[j] & 1)) upd_dw[j] = NAN;
         }
-        if (segmented) {
-            for (int64_t q = 0; q < nt; q++) {
-                int64_t k = touched[q];
-                if (gcount[k]) {
-                    w[k] += segmented == 2 ? delta[k] / (REAL)gcount[k] : delta[k];
-                    delta[k] = 0; gcount[k] = 0; last_slot[k] = -1;
-                }
-            }
-        }
+        n_updates += FN(update_batch_impl)(n, w, upd_board, upd_dw, B, segmented, &sc);
     }
-    free(upd_board); free(upd_dw); free(upd_on); free(delta); free(touched); free(gcount); free(last_slot);
+    free(upd_board); free(upd_dw); free(upd_on);
+    if (segmented) FN(scratch_free)(&sc);
     if (n_moves_out) *n_moves_out = n_moves;
     return n_updates;
 }

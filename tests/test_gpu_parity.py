@@ -1,0 +1,435 @@
+"""GPU tier (-m gpu): every kernel group called through the C-ABI (libb2048.so via 2048_b200/game2048/cabi.py)
+and compared with the CPU oracle / the reference-generated golden fixtures on identical seeded inputs.
+Integer, byte and index work: bit-exact.  Float32 values/weights: bit-exact against the oracle's float32
+restatement where the summation order is defined (evaluate, deterministic updates, B=1), and within a stated
+tolerance against the float64 reference fixtures."""
+import ctypes as C
+import importlib
+
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def eng():
+    pkg = importlib.import_module("2048_b200")
+    from game2048 import cabi, engine
+    ctx = engine.Context.get()
+    return ctx, engine, cabi
+
+
+def dev_boards(ctx, rows, orc):
+    return ctx.to_device(orc.pack_np(np.asarray(rows, dtype=np.int32)))
+
+
+def u64(t):
+    return t.cpu().numpy().view(np.uint64)
+
+
+def w_dev(ctx, fx, n, seed):
+    w = fx.flat(fx.init_weights32(n, seed)).astype(np.float32)
+    return w, ctx.to_device(w)
+
+
+# ------------------------------------------------------------------------------------------- (1) (2)
+def test_lut_matches_reference_table(eng):
+    ctx, engine, cabi = eng
+    g = load_golden("move_table.npz")
+    lut = ctx.lut.cpu().numpy().view(np.uint32)
+    lines = np.stack([(lut >> 12) & 15, (lut >> 8) & 15, (lut >> 4) & 15, lut & 15], axis=1).astype(np.uint8)
+    a, b = (lut >> 16) & 15, (lut >> 20) & 15
+    score = np.where(a > 0, 2 << a.astype(np.int64), 0) + np.where(b > 0, 2 << b.astype(np.int64), 0)
+    assert np.array_equal(lines, np.minimum(g["lines"], 15))
+    assert np.array_equal(score, g["score"].astype(np.int64))
+    assert np.array_equal((lut >> 24) & 1, g["changed"])
+    assert np.array_equal(((lut >> 25) & 1).astype(bool), (g["lines"] == 16).any(axis=1))
+
+
+def test_pack_unpack_roundtrip(eng, orc, fx):
+    ctx, engine, cabi = eng
+    rows = np.concatenate([fx.edge_boards(), fx.random_boards(5000, seed=1, max_exp=15)])
+    b = ctx.pack(rows)
+    assert np.array_equal(u64(b), orc.pack_np(rows))
+    assert np.array_equal(ctx.unpack(b).cpu().numpy(), rows)
+    assert ctx.pack(np.zeros((0, 4, 4), np.int32)).shape[0] == 0          # empty input
+
+
+def test_move4_predicates_vs_reference_fixture(eng, orc):
+    ctx, engine, cabi = eng
+    g = load_golden("boards.npz")
+    rows = g["boards"].astype(np.int32)
+    m = len(rows)
+    b = dev_boards(ctx, rows, orc)
+    after, gain, flags, over = ctx.move4(b)
+    ref_after = g["after"].astype(np.int32)
+    ovf = (ref_after > 15).any(axis=(2, 3))
+    assert np.array_equal(orc.unpack_np(u64(after).reshape(-1)).reshape(m, 4, 4, 4), np.minimum(ref_after, 15))
+    assert np.array_equal(gain.cpu().numpy().astype(np.int64), g["gain"].astype(np.int64))
+    fl = flags.cpu().numpy()
+    for d in range(4):
+        assert np.array_equal((fl >> d) & 1, g["change"][:, d])
+        assert np.array_equal(((fl >> (4 + d)) & 1).astype(bool), ovf[:, d])
+    assert np.array_equal(over.cpu().numpy(), g["over"])
+    stats, mask = ctx.board_stats(b)
+    st = stats.cpu().numpy()
+    assert np.array_equal(st[:, 0], g["n_empty"].astype(np.uint8))
+    assert np.array_equal(st[:, 1], g["n_pairs"].astype(np.uint8))
+    assert np.array_equal(st[:, 2], g["over"])
+    assert np.array_equal(st[:, 3], rows.reshape(m, -1).max(axis=1).astype(np.uint8))
+    mk = mask.cpu().numpy().view(np.uint16)
+    for q in range(0, m, 5):                      # Game.empty order = ascending flat cell = ascending bit
+        assert [p for p in range(16) if (mk[q] >> p) & 1] == [int(p) for p in g["empties"][q] if p >= 0]
+
+
+def test_move4_exhaustive_lines_all_directions(eng, orc):
+    """all 65,536 lines as a row (left/right) and as a column (up/down) vs the oracle"""
+    ctx, engine, cabi = eng
+    lines = np.arange(65536, dtype=np.uint64)
+    rows = np.stack([(lines >> 12) & 15, (lines >> 8) & 15, (lines >> 4) & 15, lines & 15], axis=1).astype(np.int32)
+    filler = np.array([[1, 2, 3, 4], [5, 6, 7, 8], [9, 10, 11, 12]], dtype=np.int32)
+    b_row = np.concatenate([np.repeat(filler[None, :1], 65536, 0), rows[:, None, :],
+                            np.repeat(filler[None, 1:], 65536, 0)], axis=1)
+    for rows4 in (b_row, np.transpose(b_row, (0, 2, 1)).copy()):
+        after, gain, flags, over = ctx.move4(dev_boards(ctx, rows4, orc))
+        ra, rs, rc = orc.pre_move_batch(rows4)
+        assert np.array_equal(orc.unpack_np(u64(after).reshape(-1)).reshape(-1, 4, 4, 4), np.minimum(ra, 15))
+        assert np.array_equal(gain.cpu().numpy().astype(np.int64), rs)
+        fl = flags.cpu().numpy()
+        assert np.array_equal(np.stack([(fl >> d) & 1 for d in range(4)], 1), rc.astype(np.uint8))
+
+
+# ------------------------------------------------------------------------------------------- (3)
+def test_spawns_vs_oracle(eng, orc, fx):
+    ctx, engine, cabi = eng
+    ids = np.arange(3000, dtype=np.uint64) * np.uint64(7) + np.uint64(2 ** 33)
+    b0 = ctx.spawn_initial(3000, seed=99, first_id=int(ids[0]), id_step=7)
+    ref0 = np.array([orc.pack_np(orc.spawn_initial(99, int(i))[None])[0] for i in ids], dtype=np.uint64)
+    assert np.array_equal(u64(b0), ref0)
+    rows = fx.random_boards(3000, seed=3)
+    rows[:5] = 1                                             # full boards -> 0xFFFF, unchanged
+    b = dev_boards(ctx, rows, orc)
+    mv = (np.arange(3000) % 300 + 1).astype(np.uint32)
+    sp = ctx.spawn_philox(b, 5, ctx.to_device(ids), ctx.to_device(mv), want_spawn=True)
+    sp = sp.cpu().numpy().view(np.uint16)
+    got = u64(b)
+    for i in range(3000):
+        new, res = orc.spawn_move(5, int(ids[i]), int(mv[i]), rows[i])
+        assert got[i] == orc.pack_np(new[None])[0]
+        assert sp[i] == (0xFFFF if res < 0 else res)
+    # replay mode (Game.replay, game_logic.py:259-260); tile 0 = skip
+    rows = fx.random_boards(1000, seed=4)
+    tile = (np.arange(1000) % 3).astype(np.uint8)
+    pos = (np.arange(1000) * 5 % 16).astype(np.uint8)
+    b = dev_boards(ctx, rows, orc)
+    ctx.spawn_replay(b, ctx.to_device(tile), ctx.to_device(pos))
+    exp = rows.copy().reshape(-1, 16)
+    sel = tile > 0
+    exp[np.nonzero(sel)[0], pos[sel]] = tile[sel]
+    assert np.array_equal(u64(b), orc.pack_np(exp))
+
+
+def test_sweep_vs_oracle(eng, orc, fx):
+    """config-5 kernel (shared-memory LUT, persistent grid) on 200k synthetic + harvested boards"""
+    ctx, engine, cabi = eng
+    g = load_golden("boards.npz")
+    rows = np.concatenate([fx.random_boards(200_000, seed=0), g["boards"].astype(np.int32)])
+    boards = orc.pack_np(rows)
+    after, gain, flags, spawned = ctx.sweep(ctx.to_device(boards), seed=42, first_index=1 << 35)
+    ra, rg, rf, rs = orc.sweep(boards, seed=42, first_index=1 << 35)
+    assert np.array_equal(u64(after), ra)
+    assert np.array_equal(gain.cpu().numpy().view(np.uint32), rg)
+    assert np.array_equal(flags.cpu().numpy(), rf)
+    assert np.array_equal(u64(spawned), rs)
+    a2, g2, f2, _ = ctx.sweep(ctx.to_device(boards[:1000]), spawn=False)       # no-spawn variant, small grid
+    assert np.array_equal(u64(a2), ra[:1000])
+
+
+# ------------------------------------------------------------------------------------------- (4)
+@pytest.mark.parametrize("n", [2, 3, 4, 5, 6])
+def test_features_and_evaluate(eng, orc, fx, n):
+    ctx, engine, cabi = eng
+    g = load_golden("boards.npz")
+    ref = g[f"f_{n}"]
+    rows = g["boards"][:len(ref)].astype(np.int32)
+    b = dev_boards(ctx, rows, orc)
+    assert np.array_equal(ctx.features(n, b).cpu().numpy(), ref)
+    assert cabi.table_offsets(n) == orc.table_offsets(n).tolist()
+    w, wd = w_dev(ctx, fx, n, 100 + n)
+    v = ctx.evaluate(n, wd, b).cpu().numpy()
+    sub = slice(0, 400)
+    v32 = orc.evaluate_batch(n, w, rows[sub])                    # float32, same order: bit-exact
+    assert np.array_equal(v[sub], v32)
+    v64 = orc.evaluate_batch(n, w.astype(np.float64), rows[sub])  # reference arithmetic
+    assert np.allclose(v[sub], v64, rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("n", [2, 3, 4, 5])
+def test_update_single_entry_is_reference_update(eng, orc, fx, n):
+    """m = 1: every mode equals QAgent.update (r_learning.py:207-214); key multiplicities from the fixture"""
+    ctx, engine, cabi = eng
+    g = load_golden("d4.npz")
+    sample = g["sample"].astype(np.int32)
+    offs = g[f"offs_{n}"]
+    nw = cabi.num_weights(n)
+    for mode in (0, 1, 2, 3):
+        for q in (0, 3, 6, 7, 12, 20):
+            wd = ctx.zeros(nw, torch.float32)
+            b = dev_boards(ctx, sample[q:q + 1], orc)
+            ctx.td_update(n, wd, b, ctx.to_device(np.array([1.0], np.float32)), mode=mode)
+            w = wd.cpu().numpy()
+            k = np.nonzero(w)[0]
+            assert np.array_equal(k, g[f"keys_{n}"][offs[q]:offs[q + 1]])
+            assert np.array_equal(w[k].astype(np.int32), g[f"counts_{n}"][offs[q]:offs[q + 1]])
+
+
+@pytest.mark.parametrize("n", [4, 6])
+def test_update_batch_modes_vs_oracle(eng, orc, fx, n):
+    """m = 3000 entries with heavy key sharing (early-game boards) and NaN holes:
+    deterministic sum / mean bit-exact vs the float32 oracle and run-to-run identical;
+    atomic sum / mean within 1e-5 relative of the float64 oracle."""
+    ctx, engine, cabi = eng
+    rs = np.random.RandomState(7)
+    rows = fx.random_boards(3000, seed=8, p_empty=0.7, max_exp=3)
+    rows[:50] = 0
+    rows[50:60] = fx.edge_boards()[:10]
+    boards = orc.pack_np(rows)
+    dw = (rs.standard_normal(3000) * 0.3).astype(np.float32)
+    dw[::17] = np.nan
+    w0, _ = w_dev(ctx, fx, n, 5)
+    bd, dd = ctx.to_device(boards), ctx.to_device(dw)
+    ref = {}
+    for rule in (1, 2):
+        w32 = w0.copy()
+        n_upd = orc.update_batch(n, w32, boards, dw, rule)
+        assert n_upd == np.isfinite(dw).sum()
+        w64 = w0.astype(np.float64)
+        orc.update_batch(n, w64, boards, dw.astype(np.float64), rule)
+        ref[rule] = (w32, w64)
+    for rule, mode in ((1, cabi.UPD_DETERMINISTIC | cabi.UPD_SUM), (2, cabi.UPD_DETERMINISTIC | cabi.UPD_MEAN)):
+        outs = []
+        for rep in range(2):
+            wd = ctx.to_device(w0)
+            ctx.td_update(n, wd, bd, dd, mode=mode)
+            outs.append(wd.cpu().numpy())
+        assert np.array_equal(outs[0], outs[1])                          # deterministic
+        assert np.array_equal(outs[0], ref[rule][0])                     # bit-exact vs oracle float32
+    for rule, mode in ((1, cabi.UPD_ATOMIC | cabi.UPD_SUM), (2, cabi.UPD_ATOMIC | cabi.UPD_MEAN)):
+        wd = ctx.to_device(w0)
+        work = ctx.td_update(n, wd, bd, dd, mode=mode)
+        got = wd.cpu().numpy()
+        w64 = ref[rule][1]
+        scale = np.abs(w64 - w0).max()
+        assert np.abs(got - w64).max() <= 1e-5 * max(scale, 1.0)         # stated tolerance
+        if mode & cabi.UPD_MEAN:
+            assert not work.any().item()                                  # workspace left all-zero
+            ctx.td_update(n, wd, bd, dd, mode=mode, work=work)            # and reusable
+    # delta buffer receives the same increments
+    wd, delta = ctx.to_device(w0), ctx.zeros(len(w0), torch.float32)
+    ctx.td_update(n, wd, bd, dd, mode=cabi.UPD_DETERMINISTIC | cabi.UPD_MEAN, delta=delta)
+    assert np.allclose(w0 + delta.cpu().numpy(), wd.cpu().numpy(), rtol=0, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------- fused loops
+def test_greedy_replay_of_reference_games(eng, orc, fx):
+    """Game.trial_run games recorded from the real reference (trained float32 weights), teacher-forced on
+    the recorded spawns: same moves, boards and scores (bit-exact); evaluate() values within 2e-6 rel."""
+    ctx, engine, cabi = eng
+    g = load_golden("greedy_n4.npz")
+    n = 4
+    w = fx.apply_sparse(fx.flat(fx.init_weights32(n, int(g["seed"]))), g["w_idx"], g["w_val"]).astype(np.float32)
+    wd = ctx.to_device(w)
+    G = len(g["odo"])
+    tiles = [g["tiles"][g["t_off"][i]:g["t_off"][i + 1]] for i in range(G)]
+    games = engine.GameBatch(G, ctx=ctx)
+    games.set_positions(orc.pack_np(g["start"].astype(np.int32)))
+    rp = engine.ReplayBuffers(ctx, tiles)
+    tdir, tval, tsp = engine.greedy_play(ctx, n, wd, games, replay=rp, trace_len=rp.len, chunk=rp.len + 2)
+    h = games.to_host()
+    tdir, tval = tdir.cpu().numpy(), tval.cpu().numpy()
+    assert np.array_equal(h["moves"], g["odo"].astype(np.uint32))
+    assert np.array_equal(h["score"].astype(np.int64), g["score"])
+    assert np.array_equal(h["board"], orc.pack_np(g["final"].astype(np.int32)))
+    assert (h["flags"] & cabi.F_DONE).all()
+    for i in range(G):
+        mv = g["moves"][g["m_off"][i]:g["m_off"][i + 1]]
+        assert np.array_equal(tdir[i, :len(mv)], mv)
+        assert (tdir[i, len(mv):] == -2).all()                            # no sentinel after trial_run
+        # the reference evaluated every valid direction; the kernel's trace holds the max per move
+        r = orc.trial_replay(n, w.astype(np.float64), g["start"][i].astype(np.int32), tiles[i])
+        assert np.allclose(tval[i, :len(mv)], r["values"], rtol=2e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("n", [4, 5, 6])
+def test_greedy_philox_vs_oracle(eng, orc, fx, n):
+    """Philox-driven greedy games: identical scores / move counts / final boards as the float32 oracle;
+    splitting the id range over two batches (sharding) changes nothing."""
+    ctx, engine, cabi = eng
+    w, wd = w_dev(ctx, fx, n, 9)
+    num = 96 if n < 6 else 32
+    ref = orc.play_philox(n, w, seed=11, first_id=1000, num=num)
+    games = engine.GameBatch(num, seed=11, ctx=ctx).init(first_id=1000)
+    engine.greedy_play(ctx, n, wd, games, chunk=64)                       # several launches per game
+    h = games.to_host()
+    assert np.array_equal(h["score"].astype(np.int64), ref["scores"])
+    assert np.array_equal(h["moves"].astype(np.int32), ref["moves"])
+    assert np.array_equal(h["board"], ref["boards"])
+    c = games.read_counters()
+    assert c["moves"] == ref["total_moves"] and c["evals"] == ref["n_eval"] and c["finished"] == num
+    assert c["score_sum"] == ref["scores"].sum() and c["active"] == 0
+    hist = np.bincount(ref["max_tile"], minlength=17)
+    assert np.array_equal(h["tile_hist"], hist)
+    a = engine.GameBatch(num // 3, seed=11, ctx=ctx).init(first_id=1000)
+    b = engine.GameBatch(num - num // 3, seed=11, ctx=ctx).init(first_id=1000 + num // 3)
+    engine.greedy_play(ctx, n, wd, a)
+    engine.greedy_play(ctx, n, wd, b)
+    assert np.array_equal(np.concatenate([a.to_host()["board"], b.to_host()["board"]]), ref["boards"])
+    # limit_tile / step_limit (trial_run arguments)
+    lim = engine.GameBatch(16, seed=11, ctx=ctx).init(first_id=1000)
+    engine.greedy_play(ctx, n, wd, lim, limit_tile=5, step_limit=40)
+    ref_l = orc.play_philox(n, w, seed=11, first_id=1000, num=16, limit_tile=5, step_limit=40)
+    assert np.array_equal(lim.to_host()["board"], ref_l["boards"])
+
+
+def _run_replay_episodes(ctx, engine, cabi, orc, g, n, wd, mode, episodes):
+    out = []
+    for i in range(episodes):
+        tiles = g["tiles"][g["t_off"][i]:g["t_off"][i + 1]]
+        games = engine.GameBatch(1, ctx=ctx)
+        games.set_positions(orc.pack_np(g["start"][i:i + 1].astype(np.int32)))
+        rp = engine.ReplayBuffers(ctx, [tiles])
+        L = rp.len + 1
+        td, tv, tw = ctx.empty((1, L), torch.int8).fill_(-2), ctx.zeros((1, L), torch.float32), ctx.zeros((1, L), torch.float32)
+        ts = ctx.zeros((1, L), torch.int16)
+        tr = engine.TDTrainer(ctx, n, wd, games, float(g["alpha"]), mode)
+        for _ in range(len(tiles) + 2):
+            tr.step(replay=rp, trace=(td, tv, tw, ts, L))
+        out.append((games.to_host(), td.cpu().numpy()[0], tv.cpu().numpy()[0], tw.cpu().numpy()[0]))
+    return out
+
+
+@pytest.mark.parametrize("n", [2, 3, 4, 5, 6])
+def test_td_episode_teacher_forced_vs_reference(eng, orc, fx, n):
+    """QAgent.episode recorded from the real reference, replayed on the GPU with B = 1 (atomic, sum):
+    moves incl. the -1 sentinel, boards, scores bit-exact; per-step dw and final weights bit-exact vs the
+    float32 oracle and within tolerance of the float64 reference (|dw err| <= 1e-4 (1 + |dw|); weights
+    <= 2e-3 absolute after all episodes)."""
+    ctx, engine, cabi = eng
+    g = load_golden(f"episodes_n{n}.npz")
+    E = min(len(g["odo"]), 12)
+    w0 = fx.flat(fx.init_weights32(n, int(g["seed"]))).astype(np.float32)
+    wd = ctx.to_device(w0)
+    res = _run_replay_episodes(ctx, engine, cabi, orc, g, n, wd, cabi.UPD_ATOMIC | cabi.UPD_SUM, E)
+    w32 = w0.copy()
+    u = 0
+    for i, (h, td, tv, tw) in enumerate(res):
+        mv = g["moves"][g["m_off"][i]:g["m_off"][i + 1]]
+        tiles = g["tiles"][g["t_off"][i]:g["t_off"][i + 1]]
+        r32 = orc.episode_replay(n, w32, float(g["alpha"]), g["start"][i].astype(np.int32), tiles)
+        odo = r32["odometer"]
+        assert np.array_equal(td[:odo + 1], r32["moves"]) and td[odo] == -1
+        assert np.array_equal(tw[1:odo + 1], r32["dws"][1:]) and np.isnan(tw[0])
+        assert np.array_equal(tv[:odo], r32["values"][:odo])
+        assert h["flags"][0] & cabi.F_DONE
+        if np.array_equal(r32["moves"], mv):                              # float32 followed the reference game
+            assert h["moves"][0] == g["odo"][i] and h["score"][0] == g["score"][i]
+            assert h["board"][0] == orc.pack_np(g["final"][i:i + 1].astype(np.int32))[0]
+            ref_dw = g["upd_dw"][u:u + odo]
+            assert np.all(np.abs(tw[1:odo + 1] - ref_dw) <= 1e-4 * (1 + np.abs(ref_dw)))
+        u += len(mv) - 1
+    assert np.array_equal(wd.cpu().numpy(), w32)                          # bit-exact vs float32 oracle
+    if E == len(g["odo"]):
+        ref_w = fx.apply_sparse(w0.astype(np.float64), g["w_idx"], g["w_val"])
+        assert np.abs(wd.cpu().numpy() - ref_w).max() <= 2e-3
+
+
+@pytest.mark.parametrize("n,B", [(4, 1), (4, 64), (5, 48), (3, 33)])
+def test_td_lockstep_deterministic_bit_exact(eng, orc, fx, n, B):
+    """Philox lock-step TD with in-place restart: deterministic modes are bit-exact vs the float32 oracle
+    (weights, boards, scores, ids, labels, counters) and run-to-run identical."""
+    ctx, engine, cabi = eng
+    steps = 300
+    for rule, mode, alpha in ((1, cabi.UPD_DETERMINISTIC | cabi.UPD_SUM, 0.25 / max(B, 4)),
+                              (2, cabi.UPD_DETERMINISTIC | cabi.UPD_MEAN, 0.25)):
+        w0 = fx.flat(fx.init_weights32(n, 31)).astype(np.float32)
+        ref_w = w0.copy()
+        ls = orc.LockStep(n, ref_w, alpha, 77, B, first_id=5, id_stride=B, segmented=rule, threads=2)
+        ls.run(steps)
+        outs = []
+        for rep in range(2):
+            wd = ctx.to_device(w0)
+            games = engine.GameBatch(B, seed=77, id_stride=B, ctx=ctx).init(first_id=5)
+            tr = engine.TDTrainer(ctx, n, wd, games, alpha, mode)
+            tr.run(steps // 2)
+            for _ in range(steps - steps // 2):
+                tr.step()
+            outs.append((wd.cpu().numpy(), games.to_host(), games.read_counters()))
+        (wa, ha, ca), (wb, hb, cb) = outs
+        assert np.array_equal(wa, wb) and np.array_equal(ha["board"], hb["board"])
+        assert np.array_equal(ha["board"], ls.board) and np.array_equal(ha["game_id"], ls.game_id)
+        assert np.array_equal(ha["score"].astype(np.int64), ls.score)
+        assert np.array_equal(ha["moves"].astype(np.int32), ls.odo)
+        assert np.array_equal(ha["old_label"], ls.old_label)
+        assert np.array_equal(wa, ref_w)
+        assert ca["updates"] == ls.n_updates and ca["moves"] == ls.n_moves
+        assert ca["finished"] == ls.fin[0] and ca["score_sum"] == ls.fin[1] and ca["moves_sum"] == ls.fin[2]
+        assert np.array_equal(ha["tile_hist"], ls.hist)
+
+
+def test_td_lockstep_atomic_within_tolerance(eng, orc, fx):
+    """atomic modes: same sums, unordered -> weights within 1e-5 (relative to the largest change) of the
+    float64 oracle over a short stable run"""
+    ctx, engine, cabi = eng
+    n, B, steps = 4, 256, 40
+    for rule, mode, alpha in ((1, cabi.UPD_ATOMIC | cabi.UPD_SUM, 0.25 / B), (2, cabi.UPD_ATOMIC | cabi.UPD_MEAN, 0.25)):
+        w0 = fx.flat(fx.init_weights32(n, 32)).astype(np.float32)
+        w64 = w0.astype(np.float64)
+        ls = orc.LockStep(n, w64, alpha, 78, B, segmented=rule, threads=4)
+        ls.run(steps)
+        wd = ctx.to_device(w0)
+        games = engine.GameBatch(B, seed=78, ctx=ctx).init()
+        engine.TDTrainer(ctx, n, wd, games, alpha, mode).run(steps)
+        got = wd.cpu().numpy()
+        scale = np.abs(w64 - w0).max()
+        assert np.abs(got - w64).max() <= 1e-4 * max(scale, 1.0)
+        assert games.read_counters()["updates"] == ls.n_updates
+
+
+def test_finished_game_log_and_delta_apply(eng, orc, fx):
+    ctx, engine, cabi = eng
+    n, B = 4, 64
+    w0 = fx.flat(fx.init_weights32(n, 33)).astype(np.float32)
+    wd = ctx.to_device(w0)
+    games = engine.GameBatch(B, seed=3, ctx=ctx, fin_cap=4096).init()
+    delta = ctx.zeros(len(w0), torch.float32)
+    tr = engine.TDTrainer(ctx, n, wd, games, 0.25, cabi.UPD_DETERMINISTIC | cabi.UPD_MEAN, delta=delta)
+    tr.run(600)
+    rec = games.drain_finished()
+    c = games.read_counters()
+    assert len(rec) == c["finished"] > 0 and rec[:, 1].sum() == c["score_sum"] and rec[:, 2].sum() == c["moves_sum"]
+    assert len(games.drain_finished()) == 0
+    # multi-GPU sync kernel: w_sync += delta_sum; w = w_sync; delta = 0
+    w_sync = ctx.to_device(w0)
+    dsum = delta.clone() * 2
+    check = w0 + 2 * delta.cpu().numpy()
+    cabi.check(ctx.lib.b2048_delta_apply(engine.dptr(wd), engine.dptr(w_sync), engine.dptr(delta), engine.dptr(dsum),
+                                         len(w0), engine.cur_stream()))
+    assert np.array_equal(wd.cpu().numpy(), check) and np.array_equal(w_sync.cpu().numpy(), check)
+    assert not delta.any().item()
+
+
+def test_argument_errors(eng):
+    ctx, engine, cabi = eng
+    L = ctx.lib
+    assert L.b2048_num_feat(7) == -1 and L.b2048_num_weights(1) == -1
+    assert L.b2048_features(7, None, 1, None, None) == -1
+    assert L.b2048_move4(None, None, 1, None, None, None, None, None) == -1
+    assert L.b2048_evaluate(4, None, None, 0, None, None) == -1
+    b = ctx.zeros(4, torch.int64)
+    assert L.b2048_td_update(4, engine.dptr(ctx.zeros(cabi.num_weights(4), torch.float32)), None, engine.dptr(b),
+                             engine.dptr(ctx.zeros(4, torch.float32)), 4, 3, None, 0, None) == -3     # EWORK
+    assert b"workspace" in L.b2048_strerror(-3)
