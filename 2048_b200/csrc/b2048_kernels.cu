@@ -530,12 +530,15 @@ __device__ __forceinline__ void warp_add_counter(uint64_t *ctr, uint32_t v)
 }
 
 __device__ __forceinline__ void log_finished(const b2048_games_t &g, uint64_t id, uint32_t score, uint32_t moves,
-                                             uint32_t max_exp)
+                                             uint32_t max_exp, uint64_t board)
 {
     if (!g.fin_log) return;
     unsigned long long idx = atomicAdd(reinterpret_cast<unsigned long long *>(g.counters + B2048_CTR_LOG), 1ULL);
-    if (int64_t(idx) < g.fin_cap)
-        reinterpret_cast<uint4 *>(g.fin_log)[idx] = make_uint4(uint32_t(id), score, moves, max_exp);
+    if (int64_t(idx) < g.fin_cap) {
+        uint4 *rec = reinterpret_cast<uint4 *>(g.fin_log) + 2 * idx;
+        rec[0] = make_uint4(uint32_t(id), uint32_t(id >> 32), score, moves);
+        rec[1] = make_uint4(max_exp, uint32_t(board), uint32_t(board >> 32), 0u);
+    }
 }
 
 // One afterstate per lane (lane d of a 4-lane group = direction d), value by n-tuple gather, then a
@@ -595,7 +598,7 @@ greedy_play_kernel(const float *__restrict__ w, const uint32_t *__restrict__ lut
                 if (d == 0) {
                     c_fin++; c_score += score; c_msum += odo;
                     atomicAdd(g.tile_hist + max_tile(board), 1u);
-                    log_finished(g, id, score, odo, max_tile(board));
+                    log_finished(g, id, score, odo, max_tile(board), board);
                 }
             }
         }
@@ -614,7 +617,7 @@ greedy_play_kernel(const float *__restrict__ w, const uint32_t *__restrict__ lut
                 if (d == 0) {
                     c_fin++; c_score += score; c_msum += odo; c_ovf++;
                     atomicAdd(g.tile_hist + 16, 1u);
-                    log_finished(g, id, score, odo, 16u);
+                    log_finished(g, id, score, odo, 16u, board);
                 }
             } else {
                 if (d == 0) {
@@ -701,14 +704,14 @@ td_phase_a_kernel(const float *__restrict__ w, const uint32_t *__restrict__ lut,
                 c_fin++; c_score += score; c_msum += odo;
                 if (!over) c_ovf++;
                 atomicAdd(g.tile_hist + (over ? max_tile(board) : 16), 1u);
-                log_finished(g, id, score, odo, over ? uint32_t(max_tile(board)) : 16u);
+                log_finished(g, id, score, odo, over ? uint32_t(max_tile(board)) : 16u, board);
                 if (trace_dir && int64_t(odo) < trace_len) {
                     trace_dir[slot * trace_len + odo] = -1;          // :247 sentinel
                     if (trace_value) trace_value[slot * trace_len + odo] = 0.0f;
                     if (trace_dw) trace_dw[slot * trace_len + odo] = dw;
                 }
             }
-            if (has_replay) {
+            if (has_replay || g.id_stride == 0) {                    // single-episode mode: stop, no restart
                 flags = (flags | B2048_F_DONE) & ~B2048_F_HAVE_STATE;
                 if (!over) flags |= B2048_F_OVERFLOW;
             } else {                                                 // in-place restart

@@ -194,7 +194,7 @@ class GameBatch:
         self.flags = z(B, U8)
         self.counters, self.tile_hist = z(cabi.CTR_COUNT, I64), z(17, I32)
         self.fin_cap = int(fin_cap)
-        self.fin_log = z((self.fin_cap, 4), I32) if self.fin_cap else None
+        self.fin_log = z((self.fin_cap, 8), I32) if self.fin_cap else None
         self.c = cabi.Games(self.B, self.board.data_ptr(), self.score.data_ptr(), self.moves.data_ptr(),
                             self.game_id.data_ptr(), self.state.data_ptr(), self.old_label.data_ptr(),
                             self.flags.data_ptr(), self.counters.data_ptr(), self.tile_hist.data_ptr(),
@@ -221,9 +221,10 @@ class GameBatch:
         return {k: int(v) for k, v in zip(names, c)}
 
     def drain_finished(self):
-        """finished-game records since the last drain: uint32 [k,4] = (id low bits, score, moves, max exp)"""
+        """finished-game records since the last drain, completion order: uint32 [k,8] =
+        (id lo, id hi, score, moves, max exponent, board lo, board hi, 0)"""
         if not self.fin_cap:
-            return np.zeros((0, 4), np.uint32)
+            return np.zeros((0, 8), np.uint32)
         head = int(self.counters[cabi.CTR_LOG].item())
         k = min(head, self.fin_cap)
         rec = self.fin_log[:k].cpu().numpy().view(np.uint32).copy()

@@ -142,9 +142,10 @@ typedef struct b2048_games {
     uint64_t *counters;   /* [B2048_CTR_COUNT] accumulated by the kernels */
     uint32_t *tile_hist;  /* [17] finished games by max exponent */
     uint64_t seed;        /* Philox key */
-    uint64_t id_stride;   /* TD in-place restart: game_id += id_stride (total slots over all ranks) */
-    uint32_t *fin_log;    /* [fin_cap,4] (game id low 32 bits, score, moves, max exponent) of finished
-                             games in completion order; head = counters[B2048_CTR_LOG]; may be NULL */
+    uint64_t id_stride;   /* TD in-place restart: game_id += id_stride (total slots over all ranks);
+                             0 = no restart: a finished slot gets B2048_F_DONE (QAgent.episode, B = 1) */
+    uint32_t *fin_log;    /* [fin_cap,8] (id lo, id hi, score, moves, max exponent, board lo, board hi, 0)
+                             of finished games in completion order; head = counters[B2048_CTR_LOG]; NULL ok */
     int64_t fin_cap;      /* records that fit; later finishes are counted but not stored */
 } b2048_games_t;
 

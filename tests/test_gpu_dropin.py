@@ -1,0 +1,138 @@
+"""GPU tier: the reference-facing Python surface (game2048.game_logic.Game, game2048.r_learning.QAgent) on top
+of the C-ABI.  These read like tests of the reference itself: same calls, same seeds, same expected results."""
+import importlib
+import os
+import pickle
+import random
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, load_golden
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+P = os.path.join(GOLDEN, "pickles")
+
+
+@pytest.fixture(scope="module")
+def mods():
+    importlib.import_module("2048_b200")
+    from game2048 import game_logic, r_learning
+    return game_logic, r_learning
+
+
+def agent_from(rl, fx, n, arrays):
+    a = rl.QAgent(name="t", storage="local", console="local", n=n, with_weights=False)
+    a.weights = arrays
+    a.np_to_list()
+    return a
+
+
+def test_game_single_board_api_vs_reference_fixture(mods, orc):
+    gl, rl = mods
+    g = load_golden("boards.npz")
+    game = gl.Game(row=np.zeros((4, 4), dtype=np.int32))
+    c0 = gl.Game.counter
+    for q in list(range(11)) + list(range(11, 3000, 97)):
+        row = g["boards"][q].astype(np.int32)
+        for d in range(4):
+            if (g["after"][q, d] > 15).any():
+                with pytest.raises(OverflowError):
+                    game.pre_move(row, 1000, d)
+                continue
+            nr, ns, ch = game.pre_move(row, 1000, d)
+            assert nr.dtype == np.int32 and nr.shape == (4, 4)
+            assert np.array_equal(nr, g["after"][q, d]) and ns == 1000 + g["gain"][q, d] and ch == bool(g["change"][q, d])
+        assert game.game_over(row) == bool(g["over"][q])
+        assert gl.Game.empty_count(row) == g["n_empty"][q] and gl.Game.adjacent_pair_count(row) == g["n_pairs"][q]
+        assert [4 * i + j for i, j in gl.Game.empty(row)] == [int(p) for p in g["empties"][q] if p >= 0]
+    assert gl.Game.counter > c0
+    t = gl.Game.table
+    assert t[(1, 1, 1, 1)] == ((2, 2, 0, 0), 8, True) and t[(1, 2, 3, 4)] == ((1, 2, 3, 4), 0, False)
+    assert t[(14, 14, 14, 14)] == ((15, 15, 0, 0), 65536, True) and len(t) == 65536
+    with pytest.raises(KeyError):
+        game.pre_move(np.full((4, 4), 16), 0, 0)              # the reference raises KeyError on a 2^16 tile
+
+
+def test_seeded_game_reproduces_reference_rng_stream(mods, fx):
+    """random.seed(s); Game(); trial_run(estimator): the single-game API consumes Python's `random` exactly like
+    the reference (randrange(10) then choice(empties)), so the recorded reference game is reproduced move by move"""
+    gl, rl = mods
+    g = load_golden("greedy_n4.npz")
+    n, seed = 4, int(g["seed"])
+    w = fx.apply_sparse(fx.flat(fx.init_weights32(n, seed)), g["w_idx"], g["w_val"]).astype(np.float32)
+    agent = agent_from(rl, fx, n, fx.unflat(n, w))
+    random.seed(seed + 2000)
+    np.random.seed(seed + 2000)
+    for i in range(2):
+        game = gl.Game()
+        assert np.array_equal(game.starting_position, g["start"][i])
+        game.trial_run(lambda row, score: agent.evaluate(row, score))     # generic estimator -> reference loop
+        assert game.moves == g["moves"][g["m_off"][i]:g["m_off"][i + 1]].tolist()
+        assert [(t, p[0], p[1]) for t, p in game.tiles] == [tuple(t) for t in g["tiles"][g["t_off"][i]:g["t_off"][i + 1]]]
+        assert game.score == g["score"][i] and game.odometer == g["odo"][i] and np.array_equal(game.row, g["final"][i])
+        chain = game.replay(verbose=False)
+        assert np.array_equal(chain[game.odometer][0], game.row) and chain[game.odometer + 1] == (None, None, -1)
+
+
+def test_agent_evaluate_update_match_reference_pickle(mods):
+    """a reference-written agent file: evaluate() on the float32 file contents (<= 1e-6 rel), update() like the
+    reference (8 images x F tables, r_learning.py:207-214)"""
+    gl, rl = mods
+    agent = rl.QAgent.load_agent_local(os.path.join(P, "ref_agent_n2.pkl"))
+    probe = np.load(os.path.join(P, "probe.npz"))
+    for row, v in zip(probe["rows"], probe["values32"]):
+        assert abs(agent.evaluate(row) - v) <= 1e-6 * max(1.0, abs(v))
+    assert np.allclose(agent.evaluate_batch(probe["rows"]), probe["values32"], rtol=1e-6)
+    before = np.concatenate([a.reshape(-1) for a in agent.list_to_np()])
+    row = probe["rows"][0]
+    agent.update(row, 0.5)
+    after = np.concatenate([a.reshape(-1) for a in agent.list_to_np()])
+    assert abs((after - before).sum() - 0.5 * 8 * 24) < 1e-3 and 0 < np.count_nonzero(after != before) <= 8 * 24
+    assert abs(agent.evaluate(row) - (probe["values32"][0] + (after - before)[rl.f_2(row) + 256 * np.arange(24)].sum())) < 1e-4
+
+
+def test_episode_returns_a_replayable_game(mods, fx):
+    gl, rl = mods
+    random.seed(5)
+    agent = agent_from(rl, fx, 4, fx.init_weights32(4, 2))
+    w0 = agent._device_weights().clone()
+    game = agent.episode()
+    assert agent.step == 1 and game.moves[-1] == -1 and len(game.moves) == game.odometer + 1
+    assert len(game.tiles) == game.odometer and game.game_over(game.row)
+    chain = game.replay(verbose=False)
+    assert np.array_equal(chain[game.odometer][0], game.row) and chain[game.odometer][1] == game.score
+    assert (agent._device_weights() != w0).sum().item() > 100
+
+
+def test_trial_and_train_run_drivers(mods, fx, tmp_path, monkeypatch, capsys):
+    gl, rl = mods
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.setenv("B2048_STORAGE", str(tmp_path / "store"))
+    np.random.seed(0)
+    random.seed(0)
+    agent = rl.QAgent(name="drv", storage="local", console="local", n=4, batch=256)
+    info = agent.train_run(num_eps=1200, saving=True)
+    out = capsys.readouterr().out
+    assert agent.step == 1201 and len(agent.train_history) == 12           # num_eps + 1 episodes, one entry per 100
+    assert "average over last 1000 episodes" in out and "agent saved in drv.pkl" in out and "new best game" in out
+    assert info["updates"] > 100_000 and os.path.exists("drv.pkl") and os.path.exists("best_of_drv.pkl")
+    assert agent.train_history[-1] > agent.train_history[0]                # it learns
+    results = rl.QAgent.trial(estimator=agent.evaluate, num=40, storage="local", game_file="best.pkl", seed=3)
+    out = capsys.readouterr().out
+    assert len(results) == 40 and results[0].score >= results[-1].score
+    assert "average score of 40 runs" in out and "time per shuffle" in out
+    best = gl.Game.load_game("best.pkl")
+    assert best.score == results[0].score and len(best.moves) == best.odometer == len(best.tiles)
+    chain = best.replay(verbose=False)
+    assert np.array_equal(chain[best.odometer][0], best.row)
+    # file round trips: local whole-object pickle and the two-object layout
+    again = rl.QAgent.load_agent_local("drv.pkl")
+    assert again.step == agent.step and torch.equal(again._device_weights(), agent._device_weights())
+    agent.s3 = True
+    agent.save_agent()
+    third = rl.QAgent.load_agent("a/drv.pkl")
+    assert third.alpha == agent.alpha and torch.equal(third._device_weights(), agent._device_weights())
+    row = results[0].row
+    assert third.evaluate(row) == agent.evaluate(row)

@@ -410,7 +410,7 @@ def test_finished_game_log_and_delta_apply(eng, orc, fx):
     tr.run(600)
     rec = games.drain_finished()
     c = games.read_counters()
-    assert len(rec) == c["finished"] > 0 and rec[:, 1].sum() == c["score_sum"] and rec[:, 2].sum() == c["moves_sum"]
+    assert len(rec) == c["finished"] > 0 and rec[:, 2].sum() == c["score_sum"] and rec[:, 3].sum() == c["moves_sum"]
     assert len(games.drain_finished()) == 0
     # multi-GPU sync kernel: w_sync += delta_sum; w = w_sync; delta = 0
     w_sync = ctx.to_device(w0)
