@@ -271,104 +271,158 @@ __global__ void evaluate_kernel(const float *__restrict__ w, const uint64_t *__r
 // red.global.add.f32 (no return value -> fire and forget)
 __device__ __forceinline__ void red_add(float *p, float v) { atomicAdd(p, v); }
 
-// atomic, sum rule: thread per (entry j, image s)
-template <int N>
-__global__ void td_update_atomic_sum_kernel(float *__restrict__ w, float *__restrict__ delta,
-                                            const uint64_t *__restrict__ boards, const float *__restrict__ dw, int64_t m)
+// ---- accumulate pass -------------------------------------------------------------------------
+// Thread per (entry j, image s); the 8 images of an entry are 8 adjacent lanes, a warp holds 4 entries.
+// For every table i the warp first merges lanes that hit the same key (__match_any_sync): hot keys
+// (empty rows/squares early in a game) would otherwise serialise thousands of same-address atomics in L2.
+//   DIRECT          atomic + sum rule: the merged contribution goes straight into w (and delta)
+//   otherwise       acc[k] += contribution (float RED, or exact int64 fixed point when EXACT),
+//                   cnt[k] += number of distinct entries (MEAN) or 1; the lane that sees cnt go 0 -> >0
+//                   appends k to the touched list, so the apply pass needs no atomics at all.
+constexpr double FIX_SCALE = 4294967296.0;      // 2^32: exact-mode contributions are llrint(dw * 2^32)
+
+struct UpdCtrl {
+    uint32_t count;     // touched keys of the running update
+    uint32_t ticket;    // apply pass: blocks done (the last one resets both)
+    uint32_t pad[2];
+};
+
+__device__ __forceinline__ long long quantize(float d) { return __double2ll_rn(double(d) * FIX_SCALE); }
+
+__device__ __forceinline__ void accumulate_key(bool exact, void *__restrict__ acc, uint32_t *__restrict__ cnt,
+                                               uint32_t *__restrict__ touched, UpdCtrl *__restrict__ ctrl, int64_t k,
+                                               float fsum, long long qsum, uint32_t nfirst)
 {
-    int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
-    int64_t j = t >> 3;
-    if (j >= m) return;
-    float d = __ldg(dw + j);
-    if (isnan(d)) return;
-    uint64_t b = d4_image(__ldg(boards + j), int(t & 7));
-    uint64_t y = (N == 6) ? clamp13(b) : 0;
-    for_each_feature<N>([&](auto I) {
-        constexpr int i = decltype(I)::value;
-        int64_t k = table_offset(N, i) + feat_index<N, i>(b, y);
-        red_add(w + k, d);
-        if (delta) red_add(delta + k, d);
-    });
+    if (exact)
+        atomicAdd(reinterpret_cast<unsigned long long *>(acc) + k, (unsigned long long)qsum);
+    else
+        atomicAdd(reinterpret_cast<float *>(acc) + k, fsum);
+    uint32_t old = atomicAdd(cnt + k, nfirst);
+    if (old == 0) touched[atomicAdd(&ctrl->count, 1u)] = uint32_t(k);
 }
 
-// atomic, per-key-mean rule, pass 1: acc[k] += dw per contribution, cnt[k] += 1 per DISTINCT entry
-// (a key can repeat among the 8 images of one board: only the first image holding it counts).
-// Thread per (entry, image); the 8 images of an entry are 8 adjacent lanes.
-template <int N>
-__global__ void td_update_mean_accum_kernel(float *__restrict__ acc, uint32_t *__restrict__ cnt,
-                                            const uint64_t *__restrict__ boards, const float *__restrict__ dw, int64_t m)
+template <int N, bool EXACT, bool MEAN, bool DIRECT>
+__global__ void __launch_bounds__(128)
+td_accum_kernel(float *__restrict__ w, float *__restrict__ delta, void *__restrict__ acc, uint32_t *__restrict__ cnt,
+                uint32_t *__restrict__ touched, UpdCtrl *__restrict__ ctrl, const uint64_t *__restrict__ boards,
+                const float *__restrict__ dw, int64_t m)
 {
-    int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
-    int64_t j = t >> 3;
-    const int s = int(t & 7);
+    const int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    const int64_t j = t >> 3;
+    const int s = int(t & 7), lane = threadIdx.x & 31;
     const bool on = j < m;
-    float d = on ? __ldg(dw + j) : NAN;
-    const bool live = on && !isnan(d);
-    uint64_t b = d4_image(on ? __ldg(boards + j) : 0, s);
-    uint64_t y = (N == 6) ? clamp13(b) : 0;
+    const float d = on ? __ldg(dw + j) : NAN;
+    const bool live = on && (EXACT ? isfinite(d) : !isnan(d));
+    if (!__any_sync(FULL, live)) return;
+    const uint64_t b = d4_image(on ? __ldg(boards + j) : 0, s);
+    const uint64_t y = (N == 6) ? clamp13(b) : 0;
+    const long long q = (EXACT && live) ? quantize(d) : 0;
     for_each_feature<N>([&](auto I) {
         constexpr int i = decltype(I)::value;
-        uint32_t f = feat_index<N, i>(b, y);
-        bool first = true;
+        const uint32_t f = feat_index<N, i>(b, y);
+        const uint32_t k = uint32_t(table_offset(N, i)) + f;
+        uint32_t first = 1;
+        if (MEAN) {                                   // is a lower image of the same entry on the same key?
 #pragma unroll
-        for (int o = 1; o < 8; o++) {                 // same table, other images of the same entry
-            uint32_t fo = __shfl_xor_sync(FULL, f, o);
-            if (fo == f && (s ^ o) < s) first = false;
+            for (int o = 1; o < 8; o++) {
+                uint32_t fo = __shfl_xor_sync(FULL, f, o);
+                if (fo == f && (s ^ o) < s) first = 0;
+            }
         }
-        if (live) {
-            int64_t k = table_offset(N, i) + f;
-            red_add(acc + k, d);
-            if (first) atomicAdd(cnt + k, 1u);
+        const uint32_t peers = __match_any_sync(FULL, live ? k : 0xFFFFFFFFu - uint32_t(lane));
+        float fsum = d;
+        long long qsum = q;
+        uint32_t nf = first;
+        if (peers & (peers - 1)) {                    // more than one lane on this key: merge (group-uniform branch)
+            fsum = 0.0f; qsum = 0; nf = 0;
+            for (uint32_t mm = peers; mm; mm &= mm - 1) {
+                const int src = __ffs(mm) - 1;
+                if (EXACT) {
+                    qsum += __shfl_sync(peers, q, src);
+                } else {
+                    fsum += __shfl_sync(peers, d, src);
+                }
+                if (MEAN) nf += __shfl_sync(peers, first, src);
+            }
+            if (!MEAN) nf = 1;
+        }
+        if (live && lane == __ffs(peers) - 1) {
+            if (DIRECT) {
+                atomicAdd(w + k, fsum);
+                if (delta) atomicAdd(delta + k, fsum);
+            } else {
+                accumulate_key(EXACT, acc, cnt, touched, ctrl, k, fsum, qsum, nf);
+            }
         }
     });
 }
 
-// pass 2: whoever swaps the count out applies  w[k] += acc[k] / cnt  and clears acc[k]
-template <int N>
-__global__ void td_update_mean_apply_kernel(float *__restrict__ w, float *__restrict__ delta, float *__restrict__ acc,
-                                            uint32_t *__restrict__ cnt, const uint64_t *__restrict__ boards,
-                                            const float *__restrict__ dw, int64_t m)
+// ---- apply pass: one thread per touched key, plain loads/stores --------------------------------
+template <bool EXACT, bool MEAN>
+__global__ void __launch_bounds__(256)
+td_apply_kernel(float *__restrict__ w, float *__restrict__ delta, void *__restrict__ acc, uint32_t *__restrict__ cnt,
+                const uint32_t *__restrict__ touched, UpdCtrl *__restrict__ ctrl)
 {
-    int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
-    int64_t j = t >> 3;
-    if (j >= m) return;
-    float d = __ldg(dw + j);
-    if (isnan(d)) return;
-    uint64_t b = d4_image(__ldg(boards + j), int(t & 7));
-    uint64_t y = (N == 6) ? clamp13(b) : 0;
-    for_each_feature<N>([&](auto I) {
-        constexpr int i = decltype(I)::value;
-        int64_t k = table_offset(N, i) + feat_index<N, i>(b, y);
-        uint32_t c = atomicExch(cnt + k, 0u);
-        if (c) {
-            float u = __fdiv_rn(acc[k], float(c));
-            acc[k] = 0.0f;
-            w[k] = __fadd_rn(w[k], u);
-            if (delta) delta[k] = __fadd_rn(delta[k], u);
+    const uint32_t count = *reinterpret_cast<volatile uint32_t *>(&ctrl->count);
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < count; t += gridDim.x * blockDim.x) {
+        const uint32_t k = touched[t];
+        const uint32_t c = cnt[k];
+        float u;
+        if (EXACT) {
+            long long qs = reinterpret_cast<long long *>(acc)[k];
+            double x = double(qs) / FIX_SCALE;
+            if (MEAN) x = x / double(c);
+            u = __double2float_rn(x);
+            reinterpret_cast<long long *>(acc)[k] = 0;
+        } else {
+            float fs = reinterpret_cast<float *>(acc)[k];
+            u = MEAN ? __fdiv_rn(fs, float(c)) : fs;
+            reinterpret_cast<float *>(acc)[k] = 0.0f;
         }
-    });
+        cnt[k] = 0;
+        w[k] = __fadd_rn(w[k], u);
+        if (delta) delta[k] = __fadd_rn(delta[k], u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&ctrl->ticket, 1u) == gridDim.x - 1) {       // last block: ready for the next update
+            ctrl->count = 0;
+            ctrl->ticket = 0;
+        }
+    }
 }
 
-// deterministic: key generation -> stable LSD radix sort of (key, entry) -> per-key sequential sums
+// deterministic, SORTED variant: key generation -> stable LSD radix sort of (key, entry | first << 31) ->
+// chunked per-key partial sums (exact int64) -> the same acc/cnt/touched/apply tail as the direct variant
 template <int N>
 __global__ void td_keys_kernel(const uint64_t *__restrict__ boards, const float *__restrict__ dw, int64_t m,
                                uint32_t *__restrict__ keys, uint32_t *__restrict__ vals)
 {
     int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
     int64_t j = t >> 3;
-    if (j >= m) return;
     constexpr int F = num_feat(N);
     const int s = int(t & 7);
-    float d = __ldg(dw + j);
-    const bool live = !isnan(d);
-    uint64_t b = d4_image(__ldg(boards + j), s);
+    const bool on = j < m;
+    float d = on ? __ldg(dw + j) : NAN;
+    const bool live = on && isfinite(d);
+    uint64_t b = d4_image(on ? __ldg(boards + j) : 0, s);
     uint64_t y = (N == 6) ? clamp13(b) : 0;
     uint32_t *ko = keys + (j * 8 + s) * F;
     uint32_t *vo = vals + (j * 8 + s) * F;
     for_each_feature<N>([&](auto I) {
         constexpr int i = decltype(I)::value;
-        ko[i] = live ? uint32_t(table_offset(N, i) + feat_index<N, i>(b, y)) : 0xFFFFFFFFu;
-        vo[i] = uint32_t(j);
+        const uint32_t f = feat_index<N, i>(b, y);
+        uint32_t first = 1;
+#pragma unroll
+        for (int o = 1; o < 8; o++) {
+            uint32_t fo = __shfl_xor_sync(FULL, f, o);
+            if (fo == f && (s ^ o) < s) first = 0;
+        }
+        if (on) {
+            ko[i] = live ? uint32_t(table_offset(N, i)) + f : 0xFFFFFFFFu;
+            vo[i] = uint32_t(j) | (first << 31);
+        }
     });
 }
 
@@ -474,27 +528,39 @@ radix_scatter_kernel(const uint32_t *__restrict__ kin, const uint32_t *__restric
     }
 }
 
-// sorted (key, entry): the thread at the head of each key run sums its contributions in order
-__global__ void td_segment_apply_kernel(float *__restrict__ w, float *__restrict__ delta,
-                                        const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals,
-                                        const float *__restrict__ dw, int64_t M, int mean)
+// sorted (key, value): every run of equal keys is cut into chunks of <= SEG_CHUNK positions; the thread at the
+// head of a chunk sums it (exact int64, so the association order is irrelevant) and merges it into acc/cnt
+constexpr int SEG_CHUNK = 32;
+
+template <bool MEAN>
+__global__ void td_sorted_accum_kernel(void *__restrict__ acc, uint32_t *__restrict__ cnt, uint32_t *__restrict__ touched,
+                                       UpdCtrl *__restrict__ ctrl, const uint32_t *__restrict__ keys,
+                                       const uint32_t *__restrict__ vals, const float *__restrict__ dw, int64_t M)
 {
     int64_t p = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
     if (p >= M) return;
-    uint32_t k = __ldg(keys + p);
+    const uint32_t k = __ldg(keys + p);
     if (k == 0xFFFFFFFFu) return;
-    if (p > 0 && __ldg(keys + p - 1) == k) return;
-    float s = 0.0f;
-    uint32_t g = 0, last = 0xFFFFFFFFu;
-    for (int64_t q = p; q < M && __ldg(keys + q) == k; q++) {
-        uint32_t j = __ldg(vals + q);
-        s = __fadd_rn(s, __ldg(dw + j));
-        g += (j != last);
-        last = j;
+    if ((p % SEG_CHUNK) != 0 && __ldg(keys + p - 1) == k) return;
+    const int64_t end = (p / SEG_CHUNK + 1) * SEG_CHUNK < M ? (p / SEG_CHUNK + 1) * SEG_CHUNK : M;
+    long long qs = 0;
+    uint32_t nf = 0;
+    for (int64_t q = p; q < end && __ldg(keys + q) == k; q++) {
+        const uint32_t v = __ldg(vals + q);
+        qs += quantize(__ldg(dw + (v & 0x7FFFFFFFu)));
+        nf += v >> 31;
     }
-    float u = mean ? __fdiv_rn(s, float(g)) : s;
-    w[k] = __fadd_rn(w[k], u);
-    if (delta) delta[k] = __fadd_rn(delta[k], u);
+    // a chunk that continues a run started in an earlier chunk may hold no 'first' contribution: it must not
+    // be mistaken for an untouched key, so the touched marker is "count of contributions" when !MEAN
+    if (MEAN) {
+        atomicAdd(reinterpret_cast<unsigned long long *>(acc) + k, (unsigned long long)qs);
+        const bool run_head = (p == 0) || __ldg(keys + p - 1) != k;
+        uint32_t old = atomicAdd(cnt + k, nf);
+        (void)old;
+        if (run_head) touched[atomicAdd(&ctrl->count, 1u)] = k;       // exactly one head per key run
+    } else {
+        accumulate_key(true, acc, cnt, touched, ctrl, k, 0.0f, qs, 1u);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -819,26 +885,35 @@ inline int key_bits(int n)
     return b;
 }
 
-struct DetLayout {
-    int64_t M;          // keys
-    int nblocks;
-    size_t keys_a, keys_b, vals_a, vals_b, hist, acc, cnt, total;
+struct WorkLayout {
+    int64_t M, nw;      // contributions, weights
+    int nblocks;        // sort tiles
+    size_t acc, cnt, touched, ctrl, keys_a, keys_b, vals_a, vals_b, hist, total;
 };
 
 inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
-inline DetLayout det_layout(int n, int64_t m)
+inline WorkLayout work_layout(int n, int64_t m, int mode)
 {
-    DetLayout L{};
+    WorkLayout L{};
     L.M = m * 8 * num_feat(n);
+    L.nw = table_offset(n, num_feat(n));
     L.nblocks = int(cdiv(L.M, SORT_TILE));
-    size_t kb = align256(size_t(L.M) * 4);
     size_t o = 0;
-    L.keys_a = o; o += kb;
-    L.keys_b = o; o += kb;
-    L.vals_a = o; o += kb;
-    L.vals_b = o; o += kb;
-    L.hist = o; o += align256(size_t(256) * size_t(L.nblocks > 0 ? L.nblocks : 1) * 4);
+    if (mode == (B2048_UPD_ATOMIC | B2048_UPD_SUM)) { L.total = 0; return L; }
+    L.ctrl = o; o += 256;
+    L.acc = o; o += align256(size_t(L.nw) * 8);
+    L.cnt = o; o += align256(size_t(L.nw) * 4);
+    int64_t cap = L.M < L.nw ? L.M : L.nw;
+    L.touched = o; o += align256(size_t(cap > 0 ? cap : 1) * 4);
+    if (mode & B2048_UPD_SORTED) {
+        size_t kb = align256(size_t(L.M > 0 ? L.M : 1) * 4);
+        L.keys_a = o; o += kb;
+        L.keys_b = o; o += kb;
+        L.vals_a = o; o += kb;
+        L.vals_b = o; o += kb;
+        L.hist = o; o += align256(size_t(256) * size_t(L.nblocks > 0 ? L.nblocks : 1) * 4);
+    }
     L.total = o;
     return L;
 }
@@ -853,51 +928,64 @@ int radix_pass(const uint32_t *kin, const uint32_t *vin, uint32_t *kout, uint32_
     return launch_status();
 }
 
+template <int N, bool EXACT, bool MEAN, bool DIRECT>
+void launch_accum(unsigned grid, cudaStream_t st, float *w, float *delta, void *acc, uint32_t *cnt, uint32_t *touched,
+                  UpdCtrl *ctrl, const uint64_t *boards, const float *dw, int64_t m)
+{
+    td_accum_kernel<N, EXACT, MEAN, DIRECT><<<grid, 128, 0, st>>>(w, delta, acc, cnt, touched, ctrl, boards, dw, m);
+}
+
 int td_update_impl(int n, float *weights, float *delta, const uint64_t *boards, const float *dw, int64_t m, int mode,
                    void *work, size_t work_bytes, cudaStream_t st)
 {
     if (m == 0) return 0;
-    const bool det = mode & B2048_UPD_DETERMINISTIC, mean = mode & B2048_UPD_MEAN;
-    const int64_t threads = m * 8;
-    const int blk = 128;
-    const unsigned grid = unsigned(cdiv(threads, blk));
+    const bool det = mode & B2048_UPD_DETERMINISTIC, mean = mode & B2048_UPD_MEAN, sorted = mode & B2048_UPD_SORTED;
+    if (sorted && !det) return B2048_EINVAL;
+    const unsigned grid = unsigned(cdiv(m * 8, 128));
     if (!det && !mean) {
-        DISPATCH_N(n, td_update_atomic_sum_kernel<N><<<grid, blk, 0, st>>>(weights, delta, boards, dw, m));
+        DISPATCH_N(n, launch_accum<N, false, false, true>(grid, st, weights, delta, nullptr, nullptr, nullptr, nullptr,
+                                                          boards, dw, m));
         return launch_status();
     }
-    if (!det) {
-        // workspace = acc (float) + cnt (uint32), both num_weights long and all-zero between calls
-        const int64_t nw = table_offset(n, num_feat(n));
-        if (!work || work_bytes < size_t(nw) * 8) return B2048_EWORK;
-        float *acc = reinterpret_cast<float *>(work);
-        uint32_t *cnt = reinterpret_cast<uint32_t *>(acc + nw);
-        DISPATCH_N(n, td_update_mean_accum_kernel<N><<<grid, blk, 0, st>>>(acc, cnt, boards, dw, m));
-        DISPATCH_N(n, td_update_mean_apply_kernel<N><<<grid, blk, 0, st>>>(weights, delta, acc, cnt, boards, dw, m));
-        return launch_status();
-    }
-    DetLayout L = det_layout(n, m);
+    WorkLayout L = work_layout(n, m, mode);
     if (!work || work_bytes < L.total) return B2048_EWORK;
     unsigned char *base = reinterpret_cast<unsigned char *>(work);
-    uint32_t *ka = reinterpret_cast<uint32_t *>(base + L.keys_a), *kb = reinterpret_cast<uint32_t *>(base + L.keys_b);
-    uint32_t *va = reinterpret_cast<uint32_t *>(base + L.vals_a), *vb = reinterpret_cast<uint32_t *>(base + L.vals_b);
-    uint32_t *hist = reinterpret_cast<uint32_t *>(base + L.hist);
-    DISPATCH_N(n, td_keys_kernel<N><<<grid, blk, 0, st>>>(boards, dw, m, ka, va));
-    const int bits = key_bits(n);
-    const int passes = (bits + 7) / 8;
-    const int per = (bits + passes - 1) / passes;       // digit width 5..8, equal for all passes
-    int shift = 0, rc = 0;
-    for (int p = 0; p < passes && !rc; p++, shift += per) {
-        switch (per) {
-        case 8: rc = radix_pass<8>(ka, va, kb, vb, hist, L.M, shift, L.nblocks, st); break;
-        case 7: rc = radix_pass<7>(ka, va, kb, vb, hist, L.M, shift, L.nblocks, st); break;
-        case 6: rc = radix_pass<6>(ka, va, kb, vb, hist, L.M, shift, L.nblocks, st); break;
-        default: rc = radix_pass<5>(ka, va, kb, vb, hist, L.M, shift, L.nblocks, st); break;
+    void *acc = base + L.acc;
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(base + L.cnt), *touched = reinterpret_cast<uint32_t *>(base + L.touched);
+    UpdCtrl *ctrl = reinterpret_cast<UpdCtrl *>(base + L.ctrl);
+    if (!sorted) {
+        if (det && mean) { DISPATCH_N(n, launch_accum<N, true, true, false>(grid, st, weights, delta, acc, cnt, touched, ctrl, boards, dw, m)); }
+        else if (det)    { DISPATCH_N(n, launch_accum<N, true, false, false>(grid, st, weights, delta, acc, cnt, touched, ctrl, boards, dw, m)); }
+        else             { DISPATCH_N(n, launch_accum<N, false, true, false>(grid, st, weights, delta, acc, cnt, touched, ctrl, boards, dw, m)); }
+    } else {
+        uint32_t *ka = reinterpret_cast<uint32_t *>(base + L.keys_a), *kb = reinterpret_cast<uint32_t *>(base + L.keys_b);
+        uint32_t *va = reinterpret_cast<uint32_t *>(base + L.vals_a), *vb = reinterpret_cast<uint32_t *>(base + L.vals_b);
+        uint32_t *hist = reinterpret_cast<uint32_t *>(base + L.hist);
+        DISPATCH_N(n, td_keys_kernel<N><<<grid, 128, 0, st>>>(boards, dw, m, ka, va));
+        const int bits = key_bits(n);
+        const int passes = (bits + 7) / 8;
+        const int per = (bits + passes - 1) / passes;       // digit width, equal for all passes
+        int shift = 0, rc = 0;
+        for (int p = 0; p < passes && !rc; p++, shift += per) {
+            switch (per) {
+            case 8: rc = radix_pass<8>(ka, va, kb, vb, hist, L.M, shift, L.nblocks, st); break;
+            case 7: rc = radix_pass<7>(ka, va, kb, vb, hist, L.M, shift, L.nblocks, st); break;
+            case 6: rc = radix_pass<6>(ka, va, kb, vb, hist, L.M, shift, L.nblocks, st); break;
+            default: rc = radix_pass<5>(ka, va, kb, vb, hist, L.M, shift, L.nblocks, st); break;
+            }
+            uint32_t *tk = ka; ka = kb; kb = tk;
+            uint32_t *tv = va; va = vb; vb = tv;
         }
-        uint32_t *tk = ka; ka = kb; kb = tk;
-        uint32_t *tv = va; va = vb; vb = tv;
+        if (rc) return rc;
+        if (mean) td_sorted_accum_kernel<true><<<unsigned(cdiv(L.M, 256)), 256, 0, st>>>(acc, cnt, touched, ctrl, ka, va, dw, L.M);
+        else      td_sorted_accum_kernel<false><<<unsigned(cdiv(L.M, 256)), 256, 0, st>>>(acc, cnt, touched, ctrl, ka, va, dw, L.M);
     }
+    int rc = launch_status();
     if (rc) return rc;
-    td_segment_apply_kernel<<<unsigned(cdiv(L.M, 256)), 256, 0, st>>>(weights, delta, ka, va, dw, L.M, mean ? 1 : 0);
+    const unsigned agrid = unsigned(2 * sm_count());
+    if (det && mean)  td_apply_kernel<true, true><<<agrid, 256, 0, st>>>(weights, delta, acc, cnt, touched, ctrl);
+    else if (det)     td_apply_kernel<true, false><<<agrid, 256, 0, st>>>(weights, delta, acc, cnt, touched, ctrl);
+    else              td_apply_kernel<false, true><<<agrid, 256, 0, st>>>(weights, delta, acc, cnt, touched, ctrl);
     return launch_status();
 }
 
@@ -1046,15 +1134,13 @@ int b2048_evaluate(int n, const float *weights, const uint64_t *boards, int64_t 
 size_t b2048_td_update_workspace(int n, int64_t m, int mode)
 {
     if (num_feat(n) < 0 || m < 0) return 0;
-    if (mode & B2048_UPD_DETERMINISTIC) return det_layout(n, m).total;
-    if (mode & B2048_UPD_MEAN) return size_t(table_offset(n, num_feat(n))) * 8;
-    return 0;
+    return work_layout(n, m, mode).total;
 }
 
 int b2048_td_update(int n, float *weights, float *delta, const uint64_t *boards, const float *dw, int64_t m, int mode,
                     void *work, size_t work_bytes, b2048_stream_t stream)
 {
-    if (m < 0 || num_feat(n) < 0 || !weights || (m && (!boards || !dw)) || (mode & ~3)) return B2048_EINVAL;
+    if (m < 0 || num_feat(n) < 0 || !weights || (m && (!boards || !dw)) || (mode & ~7)) return B2048_EINVAL;
     return td_update_impl(n, weights, delta, boards, dw, m, mode, work, work_bytes, S(stream));
 }
 
@@ -1104,7 +1190,7 @@ int b2048_td_step(int n, float *weights, float *delta, const uint32_t *lut, cons
                   const b2048_replay_t *replay, int8_t *trace_dir, float *trace_value, float *trace_dw,
                   uint16_t *trace_spawn, int64_t trace_len, b2048_stream_t stream)
 {
-    if (mode & ~3) return B2048_EINVAL;
+    if (mode & ~7) return B2048_EINVAL;
     int rc = b2048_td_phase_a(n, weights, lut, g, alpha, upd_board, upd_dw, replay, trace_dir, trace_value, trace_dw,
                               trace_spawn, trace_len, stream);
     if (rc || g->B == 0) return rc;

@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(os.path.dirname(_HERE), "libb2048.so")
 
-UPD_ATOMIC, UPD_DETERMINISTIC, UPD_SUM, UPD_MEAN = 0, 1, 0, 2
+UPD_ATOMIC, UPD_DETERMINISTIC, UPD_SUM, UPD_MEAN, UPD_SORTED = 0, 1, 0, 2, 4
 F_HAVE_STATE, F_DONE, F_OVERFLOW = 1, 2, 4
 (CTR_MOVES, CTR_EVALS, CTR_UPDATES, CTR_FINISHED, CTR_SCORE_SUM, CTR_MOVES_SUM, CTR_OVERFLOW, CTR_ACTIVE,
  CTR_LOG) = range(9)

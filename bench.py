@@ -78,7 +78,16 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def wait_first(self, timeout=5.0):
+        t0 = time.time()
+        while self.proc and not self.lines and time.time() - t0 < timeout:
+            time.sleep(0.05)
+
+    def mark(self):
+        """start of the timed region: only samples taken after this call are reported"""
+        self.t_mark = time.time()
 
     def stop(self):
         if not self.proc:
@@ -89,7 +98,9 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        t_mark = getattr(self, "t_mark", 0.0)
+        timed = [ln for ts, ln in self.lines if ts >= t_mark]
+        for ln in (timed or [ln for _, ln in self.lines[-3:]]):
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 8:
                 continue
@@ -203,7 +214,7 @@ def run_td(args):
     dsum = ctx.zeros(wd.numel(), torch.float32) if world > 1 else None
     tr = engine.TDTrainer(ctx, n, wd, games, args.alpha, mode, delta=delta)
     flush = ctx.zeros(64 << 20, torch.int32)                     # 256 MiB > 126 MB L2
-    launches_per_lockstep = {0: 2, 2: 3}.get(mode, None)
+    launches_per_lockstep = {0: 2, 2: 3, 1: 3, 3: 3}.get(mode, None)
 
     def step():
         if world == 1:
@@ -226,13 +237,15 @@ def run_td(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        sampler.wait_first()
     for _ in range(args.warmup):
         step()
     barrier()
     c0 = games.read_counters()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    sampler.mark()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     for a, b in ev:
@@ -341,6 +354,7 @@ def td_extras(args, ctx, engine, cabi, wd):
         return a.elapsed_time(b) * 1e-3
 
     for name, mode in (("deterministic_mean", cabi.UPD_DETERMINISTIC | cabi.UPD_MEAN),
+                       ("deterministic_mean_sorted", cabi.UPD_DETERMINISTIC | cabi.UPD_MEAN | cabi.UPD_SORTED),
                        ("atomic_sum", cabi.UPD_ATOMIC | cabi.UPD_SUM)):
         w2 = wd.clone()
         g2 = engine.GameBatch(B, seed=1, ctx=ctx).init()

@@ -108,22 +108,28 @@ int b2048_evaluate(int n, const float *weights, const uint64_t *boards, int64_t 
 /* QAgent.update, r_learning.py:207-214, for m (board, dw) entries sharing one table set: for the 8
  * D4 images of each board, weights[table][index] += dw.  Entries whose dw is NaN are skipped.
  * mode = execution | rule:
- *   B2048_UPD_ATOMIC         red.global.add.f32, unordered
- *   B2048_UPD_DETERMINISTIC  (key, entry) pairs are radix-sorted by key (stable), each key's
- *                            contributions are summed in ascending entry order (sequential float32
- *                            from 0) and applied once -> run-to-run bit-identical
+ *   B2048_UPD_ATOMIC         float32 red.global.add, unordered (run-to-run differences of a few ulp)
+ *   B2048_UPD_DETERMINISTIC  exact segmented reduction by key: every contribution is quantised to
+ *                            llrint(dw * 2^32) and summed per key in int64, which is order-independent,
+ *                            so the result is bit-identical run to run, GPU to GPU and to the CPU
+ *                            restatement; applied once per key as float((double)Q / 2^32 [/ G]).
+ *                            Non-finite dw are skipped.
+ *   | B2048_UPD_SORTED       (with DETERMINISTIC) do the reduction by key as radix sort of (key, entry)
+ *                            + chunked segmented sums instead of directly with int64 atomics; same bits
  *   B2048_UPD_SUM            w[k] += S[k], S[k] = sum of the contributions to key k (the reference
- *                            rule; exactly QAgent.update when m == 1)
+ *                            rule; QAgent.update when m == 1)
  *   B2048_UPD_MEAN           w[k] += S[k] / G[k], G[k] = number of DISTINCT entries contributing to
  *                            k: the batched rule that stays stable at the reference's alpha when
  *                            many games hit the same key in one lock-step; == SUM at m == 1
+ * Within a warp, lanes that hit the same key are merged before the atomic (hot keys such as empty rows).
  * delta (may be NULL) receives the same increments as weights (multi-GPU delta buffer).
- * work: b2048_td_update_workspace(n, m, mode) bytes; for ATOMIC|MEAN it must be all-zero on first
+ * work: b2048_td_update_workspace(n, m, mode) bytes (0 for ATOMIC|SUM); it must be all-zero on first
  * use and is left all-zero by every call. */
 #define B2048_UPD_ATOMIC 0
 #define B2048_UPD_DETERMINISTIC 1
 #define B2048_UPD_SUM 0
 #define B2048_UPD_MEAN 2
+#define B2048_UPD_SORTED 4
 size_t b2048_td_update_workspace(int n, int64_t m, int mode);
 int b2048_td_update(int n, float *weights, float *delta, const uint64_t *boards, const float *dw, int64_t m, int mode,
                     void *work, size_t work_bytes, b2048_stream_t stream);

@@ -224,10 +224,14 @@ int64_t FN(orc_play_philox)(int n, const REAL *w, uint64_t seed, uint64_t first_
  *   0 : w[k] += dw one contribution at a time, entry order, reference key order (QAgent.update x m)
  *   1 : S[k] = sequential sum (from 0) of the contributions to k in entry order;  w[k] += S[k]
  *   2 : as 1 but w[k] += S[k] / G[k], G[k] = number of distinct entries contributing to k
+ *   3 : exact fixed point (the device's DETERMINISTIC mode): Q[k] = sum of llrint(dw * 2^32) over the
+ *       contributions (int64, order-independent);  w[k] += (REAL)((double)Q[k] / 2^32)
+ *   4 : as 3 but w[k] += (REAL)((double)Q[k] / 2^32 / G[k])
+ *       non-finite dw are skipped in rules 3/4
  * scratch: NULL, or {delta[num_weights] zeros, gcount[num_weights] zeros, last[num_weights] = -1,
  * touched[m*8*F]} kept clean across calls (used by orc_td_lockstep to avoid reallocating).
  */
-typedef struct { REAL *delta; int32_t *gcount; int32_t *last; int64_t *touched; } FN(orc_scratch);
+typedef struct { REAL *delta; int32_t *gcount; int32_t *last; int64_t *touched; int64_t *qsum; } FN(orc_scratch);
 
 static void FN(scratch_alloc)(FN(orc_scratch) *sc, int n, int64_t m)
 {
@@ -237,11 +241,12 @@ static void FN(scratch_alloc)(FN(orc_scratch) *sc, int n, int64_t m)
     sc->last = (int32_t *)malloc(nw * sizeof(int32_t));
     memset(sc->last, 0xff, nw * sizeof(int32_t));
     sc->touched = (int64_t *)malloc(sizeof(int64_t) * (size_t)(m > 0 ? m : 1) * 8 * ORC_MAX_FEAT);
+    sc->qsum = (int64_t *)calloc(nw, sizeof(int64_t));
 }
 
 static void FN(scratch_free)(FN(orc_scratch) *sc)
 {
-    free(sc->delta); free(sc->gcount); free(sc->last); free(sc->touched);
+    free(sc->delta); free(sc->gcount); free(sc->last); free(sc->touched); free(sc->qsum);
 }
 
 static int64_t FN(update_batch_impl)(int n, REAL *w, const uint64_t *boards, const REAL *dw, int64_t m, int rule,
@@ -250,6 +255,7 @@ static int64_t FN(update_batch_impl)(int n, REAL *w, const uint64_t *boards, con
     int64_t n_upd = 0, nt = 0;
     for (int64_t j = 0; j < m; j++) {
         if (dw[j] != dw[j]) continue;                 /* NaN = no update */
+        if (rule >= 3 && !isfinite((double)dw[j])) continue;
         int32_t row[16];
         orc_unpack(boards[j], row);
         n_upd++;
@@ -258,8 +264,10 @@ static int64_t FN(update_batch_impl)(int n, REAL *w, const uint64_t *boards, con
         } else {
             int64_t keys[8 * ORC_MAX_FEAT];
             int nk = FN(orc_update_keys)(n, row, keys);
+            int64_t qd = rule >= 3 ? (int64_t)llrint((double)dw[j] * 4294967296.0) : 0;
             for (int q = 0; q < nk; q++) {
                 sc->delta[keys[q]] += dw[j];
+                sc->qsum[keys[q]] += qd;
                 if (sc->last[keys[q]] != (int32_t)j) { sc->last[keys[q]] = (int32_t)j; sc->gcount[keys[q]]++; }
                 sc->touched[nt++] = keys[q];
             }
@@ -268,8 +276,14 @@ static int64_t FN(update_batch_impl)(int n, REAL *w, const uint64_t *boards, con
     for (int64_t q = 0; q < nt; q++) {
         int64_t k = sc->touched[q];
         if (sc->gcount[k]) {
-            w[k] += rule == 2 ? sc->delta[k] / (REAL)sc->gcount[k] : sc->delta[k];
-            sc->delta[k] = 0; sc->gcount[k] = 0; sc->last[k] = -1;
+            if (rule >= 3) {
+                double u = (double)sc->qsum[k] / 4294967296.0;
+                if (rule == 4) u = u / (double)sc->gcount[k];
+                w[k] += (REAL)u;
+            } else {
+                w[k] += rule == 2 ? sc->delta[k] / (REAL)sc->gcount[k] : sc->delta[k];
+            }
+            sc->delta[k] = 0; sc->gcount[k] = 0; sc->last[k] = -1; sc->qsum[k] = 0;
         }
     }
     return n_upd;

@@ -176,7 +176,7 @@ def test_update_single_entry_is_reference_update(eng, orc, fx, n):
     sample = g["sample"].astype(np.int32)
     offs = g[f"offs_{n}"]
     nw = cabi.num_weights(n)
-    for mode in (0, 1, 2, 3):
+    for mode in (0, 1, 2, 3, 5, 7):
         for q in (0, 3, 6, 7, 12, 20):
             wd = ctx.zeros(nw, torch.float32)
             b = dev_boards(ctx, sample[q:q + 1], orc)
@@ -190,8 +190,9 @@ def test_update_single_entry_is_reference_update(eng, orc, fx, n):
 @pytest.mark.parametrize("n", [4, 6])
 def test_update_batch_modes_vs_oracle(eng, orc, fx, n):
     """m = 3000 entries with heavy key sharing (early-game boards) and NaN holes:
-    deterministic sum / mean bit-exact vs the float32 oracle and run-to-run identical;
-    atomic sum / mean within 1e-5 relative of the float64 oracle."""
+    deterministic sum / mean (exact fixed-point reduction by key), direct and SORTED implementations: bit-exact vs
+    the oracle's exact rules and run-to-run identical; atomic sum / mean within 1e-5 (relative to the largest
+    change) of the float64 sequential oracle."""
     ctx, engine, cabi = eng
     rs = np.random.RandomState(7)
     rows = fx.random_boards(3000, seed=8, p_empty=0.7, max_exp=3)
@@ -202,35 +203,37 @@ def test_update_batch_modes_vs_oracle(eng, orc, fx, n):
     dw[::17] = np.nan
     w0, _ = w_dev(ctx, fx, n, 5)
     bd, dd = ctx.to_device(boards), ctx.to_device(dw)
-    ref = {}
+    exact, seq64 = {}, {}
     for rule in (1, 2):
         w32 = w0.copy()
-        n_upd = orc.update_batch(n, w32, boards, dw, rule)
+        n_upd = orc.update_batch(n, w32, boards, dw, rule + 2)
         assert n_upd == np.isfinite(dw).sum()
+        exact[rule] = w32
         w64 = w0.astype(np.float64)
         orc.update_batch(n, w64, boards, dw.astype(np.float64), rule)
-        ref[rule] = (w32, w64)
-    for rule, mode in ((1, cabi.UPD_DETERMINISTIC | cabi.UPD_SUM), (2, cabi.UPD_DETERMINISTIC | cabi.UPD_MEAN)):
+        seq64[rule] = w64
+        assert np.abs(w32 - w64).max() <= 1e-5 * max(np.abs(w64 - w0).max(), 1.0)     # exact rule ~ sequential rule
+    D, M, S = cabi.UPD_DETERMINISTIC, cabi.UPD_MEAN, cabi.UPD_SORTED
+    for rule, mode in ((1, D), (2, D | M), (1, D | S), (2, D | M | S)):
         outs = []
         for rep in range(2):
             wd = ctx.to_device(w0)
-            ctx.td_update(n, wd, bd, dd, mode=mode)
+            work = ctx.td_update(n, wd, bd, dd, mode=mode)
             outs.append(wd.cpu().numpy())
+            assert not work.any().item()                                  # workspace left all-zero
         assert np.array_equal(outs[0], outs[1])                          # deterministic
-        assert np.array_equal(outs[0], ref[rule][0])                     # bit-exact vs oracle float32
-    for rule, mode in ((1, cabi.UPD_ATOMIC | cabi.UPD_SUM), (2, cabi.UPD_ATOMIC | cabi.UPD_MEAN)):
+        assert np.array_equal(outs[0], exact[rule])                      # bit-exact vs the oracle
+    for rule, mode in ((1, cabi.UPD_ATOMIC | cabi.UPD_SUM), (2, cabi.UPD_ATOMIC | M)):
         wd = ctx.to_device(w0)
         work = ctx.td_update(n, wd, bd, dd, mode=mode)
         got = wd.cpu().numpy()
-        w64 = ref[rule][1]
-        scale = np.abs(w64 - w0).max()
-        assert np.abs(got - w64).max() <= 1e-5 * max(scale, 1.0)         # stated tolerance
-        if mode & cabi.UPD_MEAN:
-            assert not work.any().item()                                  # workspace left all-zero
-            ctx.td_update(n, wd, bd, dd, mode=mode, work=work)            # and reusable
+        scale = np.abs(seq64[rule] - w0).max()
+        assert np.abs(got - seq64[rule]).max() <= 1e-5 * max(scale, 1.0)  # stated tolerance
+        assert not work.any().item()
+        ctx.td_update(n, wd, bd, dd, mode=mode, work=work)                # workspace is reusable
     # delta buffer receives the same increments
     wd, delta = ctx.to_device(w0), ctx.zeros(len(w0), torch.float32)
-    ctx.td_update(n, wd, bd, dd, mode=cabi.UPD_DETERMINISTIC | cabi.UPD_MEAN, delta=delta)
+    ctx.td_update(n, wd, bd, dd, mode=D | M, delta=delta)
     assert np.allclose(w0 + delta.cpu().numpy(), wd.cpu().numpy(), rtol=0, atol=1e-6)
 
 
@@ -353,8 +356,9 @@ def test_td_lockstep_deterministic_bit_exact(eng, orc, fx, n, B):
     (weights, boards, scores, ids, labels, counters) and run-to-run identical."""
     ctx, engine, cabi = eng
     steps = 300
-    for rule, mode, alpha in ((1, cabi.UPD_DETERMINISTIC | cabi.UPD_SUM, 0.25 / max(B, 4)),
-                              (2, cabi.UPD_DETERMINISTIC | cabi.UPD_MEAN, 0.25)):
+    for rule, mode, alpha in ((3, cabi.UPD_DETERMINISTIC | cabi.UPD_SUM, 0.25 / max(B, 4)),
+                              (4, cabi.UPD_DETERMINISTIC | cabi.UPD_MEAN, 0.25),
+                              (4, cabi.UPD_DETERMINISTIC | cabi.UPD_MEAN | cabi.UPD_SORTED, 0.25)):
         w0 = fx.flat(fx.init_weights32(n, 31)).astype(np.float32)
         ref_w = w0.copy()
         ls = orc.LockStep(n, ref_w, alpha, 77, B, first_id=5, id_stride=B, segmented=rule, threads=2)
@@ -432,4 +436,5 @@ def test_argument_errors(eng):
     b = ctx.zeros(4, torch.int64)
     assert L.b2048_td_update(4, engine.dptr(ctx.zeros(cabi.num_weights(4), torch.float32)), None, engine.dptr(b),
                              engine.dptr(ctx.zeros(4, torch.float32)), 4, 3, None, 0, None) == -3     # EWORK
+    assert L.b2048_td_update(4, engine.dptr(b), None, engine.dptr(b), engine.dptr(b), 4, 4, None, 0, None) == -1  # SORTED needs DETERMINISTIC
     assert b"workspace" in L.b2048_strerror(-3)
