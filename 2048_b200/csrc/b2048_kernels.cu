@@ -287,16 +287,21 @@ struct UpdCtrl {
     uint32_t pad[2];
 };
 
+// The accumulator is replicated ACC_REPLICAS(nw) times (replica = CTA index mod R): contributions are shared
+// so broadly (only 16-30 % of the keys of a lock-step are distinct) that same-address atomics, which L2
+// serialises at ~1.4 ns each, would otherwise dominate.  The apply pass sums the replicas of a touched key.
+__host__ __device__ constexpr int acc_replicas(int64_t nw) { return nw <= (int64_t(1) << 23) ? 8 : 2; }
+
 __device__ __forceinline__ long long quantize(float d) { return __double2ll_rn(double(d) * FIX_SCALE); }
 
 __device__ __forceinline__ void accumulate_key(bool exact, void *__restrict__ acc, uint32_t *__restrict__ cnt,
                                                uint32_t *__restrict__ touched, UpdCtrl *__restrict__ ctrl, int64_t k,
-                                               float fsum, long long qsum, uint32_t nfirst)
+                                               float fsum, long long qsum, uint32_t nfirst, int64_t replica_off)
 {
     if (exact)
-        atomicAdd(reinterpret_cast<unsigned long long *>(acc) + k, (unsigned long long)qsum);
+        atomicAdd(reinterpret_cast<unsigned long long *>(acc) + replica_off + k, (unsigned long long)qsum);
     else
-        atomicAdd(reinterpret_cast<float *>(acc) + k, fsum);
+        atomicAdd(reinterpret_cast<float *>(acc) + replica_off + k, fsum);
     uint32_t old = atomicAdd(cnt + k, nfirst);
     if (old == 0) touched[atomicAdd(&ctrl->count, 1u)] = uint32_t(k);
 }
@@ -317,6 +322,8 @@ td_accum_kernel(float *__restrict__ w, float *__restrict__ delta, void *__restri
     const uint64_t b = d4_image(on ? __ldg(boards + j) : 0, s);
     const uint64_t y = (N == 6) ? clamp13(b) : 0;
     const long long q = (EXACT && live) ? quantize(d) : 0;
+    constexpr int64_t NW = table_offset(N, num_feat(N));
+    const int64_t replica_off = int64_t(blockIdx.x % acc_replicas(NW)) * NW;
     for_each_feature<N>([&](auto I) {
         constexpr int i = decltype(I)::value;
         const uint32_t f = feat_index<N, i>(b, y);
@@ -351,7 +358,7 @@ td_accum_kernel(float *__restrict__ w, float *__restrict__ delta, void *__restri
                 atomicAdd(w + k, fsum);
                 if (delta) atomicAdd(delta + k, fsum);
             } else {
-                accumulate_key(EXACT, acc, cnt, touched, ctrl, k, fsum, qsum, nf);
+                accumulate_key(EXACT, acc, cnt, touched, ctrl, k, fsum, qsum, nf, replica_off);
             }
         }
     });
@@ -361,23 +368,32 @@ td_accum_kernel(float *__restrict__ w, float *__restrict__ delta, void *__restri
 template <bool EXACT, bool MEAN>
 __global__ void __launch_bounds__(256)
 td_apply_kernel(float *__restrict__ w, float *__restrict__ delta, void *__restrict__ acc, uint32_t *__restrict__ cnt,
-                const uint32_t *__restrict__ touched, UpdCtrl *__restrict__ ctrl)
+                const uint32_t *__restrict__ touched, UpdCtrl *__restrict__ ctrl, int64_t nw)
 {
+    const int R = acc_replicas(nw);
     const uint32_t count = *reinterpret_cast<volatile uint32_t *>(&ctrl->count);
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < count; t += gridDim.x * blockDim.x) {
         const uint32_t k = touched[t];
         const uint32_t c = cnt[k];
         float u;
         if (EXACT) {
-            long long qs = reinterpret_cast<long long *>(acc)[k];
+            long long *a = reinterpret_cast<long long *>(acc) + k;
+            long long qs = 0;
+            for (int r = 0; r < R; r++) {
+                long long v = a[r * nw];
+                if (v) { qs += v; a[r * nw] = 0; }
+            }
             double x = double(qs) / FIX_SCALE;
             if (MEAN) x = x / double(c);
             u = __double2float_rn(x);
-            reinterpret_cast<long long *>(acc)[k] = 0;
         } else {
-            float fs = reinterpret_cast<float *>(acc)[k];
+            float *a = reinterpret_cast<float *>(acc) + k;
+            float fs = 0.0f;
+            for (int r = 0; r < R; r++) {
+                float v = a[r * nw];
+                if (v != 0.0f) { fs += v; a[r * nw] = 0.0f; }
+            }
             u = MEAN ? __fdiv_rn(fs, float(c)) : fs;
-            reinterpret_cast<float *>(acc)[k] = 0.0f;
         }
         cnt[k] = 0;
         w[k] = __fadd_rn(w[k], u);
@@ -559,7 +575,7 @@ __global__ void td_sorted_accum_kernel(void *__restrict__ acc, uint32_t *__restr
         (void)old;
         if (run_head) touched[atomicAdd(&ctrl->count, 1u)] = k;       // exactly one head per key run
     } else {
-        accumulate_key(true, acc, cnt, touched, ctrl, k, 0.0f, qs, 1u);
+        accumulate_key(true, acc, cnt, touched, ctrl, k, 0.0f, qs, 1u, 0);
     }
 }
 
@@ -902,7 +918,7 @@ inline WorkLayout work_layout(int n, int64_t m, int mode)
     size_t o = 0;
     if (mode == (B2048_UPD_ATOMIC | B2048_UPD_SUM)) { L.total = 0; return L; }
     L.ctrl = o; o += 256;
-    L.acc = o; o += align256(size_t(L.nw) * 8);
+    L.acc = o; o += align256(size_t(L.nw) * 8 * acc_replicas(L.nw));
     L.cnt = o; o += align256(size_t(L.nw) * 4);
     int64_t cap = L.M < L.nw ? L.M : L.nw;
     L.touched = o; o += align256(size_t(cap > 0 ? cap : 1) * 4);
@@ -983,9 +999,9 @@ int td_update_impl(int n, float *weights, float *delta, const uint64_t *boards, 
     int rc = launch_status();
     if (rc) return rc;
     const unsigned agrid = unsigned(2 * sm_count());
-    if (det && mean)  td_apply_kernel<true, true><<<agrid, 256, 0, st>>>(weights, delta, acc, cnt, touched, ctrl);
-    else if (det)     td_apply_kernel<true, false><<<agrid, 256, 0, st>>>(weights, delta, acc, cnt, touched, ctrl);
-    else              td_apply_kernel<false, true><<<agrid, 256, 0, st>>>(weights, delta, acc, cnt, touched, ctrl);
+    if (det && mean)  td_apply_kernel<true, true><<<agrid, 256, 0, st>>>(weights, delta, acc, cnt, touched, ctrl, L.nw);
+    else if (det)     td_apply_kernel<true, false><<<agrid, 256, 0, st>>>(weights, delta, acc, cnt, touched, ctrl, L.nw);
+    else              td_apply_kernel<false, true><<<agrid, 256, 0, st>>>(weights, delta, acc, cnt, touched, ctrl, L.nw);
     return launch_status();
 }
 

