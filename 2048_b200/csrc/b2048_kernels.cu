@@ -323,7 +323,11 @@ td_accum_kernel(float *__restrict__ w, float *__restrict__ delta, void *__restri
     const uint64_t y = (N == 6) ? clamp13(b) : 0;
     const long long q = (EXACT && live) ? quantize(d) : 0;
     constexpr int64_t NW = table_offset(N, num_feat(N));
+    constexpr int F = num_feat(N);
     const int64_t replica_off = int64_t(blockIdx.x % acc_replicas(NW)) * NW;
+    // pass 1: all atomics of the thread are issued back to back (17-33 independent L2 round trips in flight);
+    // pass 2 consumes the returned counts.  A single loop would serialise one round trip per table.
+    uint32_t old[F], key[F];
     for_each_feature<N>([&](auto I) {
         constexpr int i = decltype(I)::value;
         const uint32_t f = feat_index<N, i>(b, y);
@@ -353,15 +357,26 @@ td_accum_kernel(float *__restrict__ w, float *__restrict__ delta, void *__restri
             }
             if (!MEAN) nf = 1;
         }
+        old[i] = 1;
+        key[i] = k;
         if (live && lane == __ffs(peers) - 1) {
             if (DIRECT) {
                 atomicAdd(w + k, fsum);
                 if (delta) atomicAdd(delta + k, fsum);
             } else {
-                accumulate_key(EXACT, acc, cnt, touched, ctrl, k, fsum, qsum, nf, replica_off);
+                if (EXACT)
+                    atomicAdd(reinterpret_cast<unsigned long long *>(acc) + replica_off + k, (unsigned long long)qsum);
+                else
+                    atomicAdd(reinterpret_cast<float *>(acc) + replica_off + k, fsum);
+                old[i] = atomicAdd(cnt + k, nf);
             }
         }
     });
+    if (!DIRECT) {
+#pragma unroll
+        for (int i = 0; i < F; i++)
+            if (old[i] == 0) touched[atomicAdd(&ctrl->count, 1u)] = key[i];
+    }
 }
 
 // ---- apply pass: one thread per touched key, plain loads/stores --------------------------------
@@ -860,24 +875,32 @@ td_phase_a_kernel(const float *__restrict__ w, const uint32_t *__restrict__ lut,
     warp_add_counter(g.counters + B2048_CTR_OVERFLOW, c_ovf);
 }
 
-__global__ void delta_apply_kernel(float *__restrict__ w, float *__restrict__ w_sync, float *__restrict__ delta,
-                                   const float *__restrict__ delta_sum, int64_t count)
+__global__ void delta_pack_kernel(const float *__restrict__ delta, float *__restrict__ packed, int64_t count)
 {
-    int64_t i = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) * 4;
-    const int64_t stride = int64_t(gridDim.x) * blockDim.x * 4;
-    for (; i + 3 < count; i += stride) {
-        float4 s = *reinterpret_cast<const float4 *>(delta_sum + i);
-        float4 v = *reinterpret_cast<float4 *>(w_sync + i);
-        v.x = __fadd_rn(v.x, s.x); v.y = __fadd_rn(v.y, s.y); v.z = __fadd_rn(v.z, s.z); v.w = __fadd_rn(v.w, s.w);
-        *reinterpret_cast<float4 *>(w_sync + i) = v;
-        *reinterpret_cast<float4 *>(w + i) = v;
-        *reinterpret_cast<float4 *>(delta + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < count; i += stride) {
+        float d = delta[i];
+        packed[i] = d;
+        packed[count + i] = d != 0.0f ? 1.0f : 0.0f;
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0)
-        for (int64_t q = count & ~int64_t(3); q < count; q++) {
-            float v = __fadd_rn(w_sync[q], delta_sum[q]);
-            w_sync[q] = v; w[q] = v; delta[q] = 0.f;
+}
+
+__global__ void delta_apply_kernel(float *__restrict__ w, float *__restrict__ w_sync, float *__restrict__ delta,
+                                   const float *__restrict__ delta_sum, const float *__restrict__ contributors,
+                                   int64_t count)
+{
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < count; i += stride) {
+        float s = delta_sum[i];
+        if (contributors) {
+            float c = contributors[i];
+            if (c > 1.0f) s = __fdiv_rn(s, c);
         }
+        float v = __fadd_rn(w_sync[i], s);
+        w_sync[i] = v;
+        w[i] = v;
+        delta[i] = 0.0f;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1226,14 +1249,23 @@ int b2048_td_run(int n, float *weights, float *delta, const uint32_t *lut, const
     return 0;
 }
 
-int b2048_delta_apply(float *weights, float *w_sync, float *delta, const float *delta_sum, int64_t count,
-                      b2048_stream_t stream)
+int b2048_delta_pack(const float *delta, float *packed, int64_t count, b2048_stream_t stream)
+{
+    if (count < 0 || (count && (!delta || !packed))) return B2048_EINVAL;
+    if (!count) return 0;
+    int64_t want = cdiv(count, 256), cap = int64_t(sm_count()) * 8;
+    delta_pack_kernel<<<unsigned(want < cap ? want : cap), 256, 0, S(stream)>>>(delta, packed, count);
+    return launch_status();
+}
+
+int b2048_delta_apply(float *weights, float *w_sync, float *delta, const float *delta_sum, const float *contributors,
+                      int64_t count, b2048_stream_t stream)
 {
     if (count < 0 || (count && (!weights || !w_sync || !delta || !delta_sum))) return B2048_EINVAL;
     if (!count) return 0;
-    int64_t want = cdiv(count, 4 * 256);
-    int64_t cap = int64_t(sm_count()) * 8;
-    delta_apply_kernel<<<unsigned(want < cap ? want : cap), 256, 0, S(stream)>>>(weights, w_sync, delta, delta_sum, count);
+    int64_t want = cdiv(count, 256), cap = int64_t(sm_count()) * 8;
+    delta_apply_kernel<<<unsigned(want < cap ? want : cap), 256, 0, S(stream)>>>(weights, w_sync, delta, delta_sum,
+                                                                              contributors, count);
     return launch_status();
 }
 

@@ -64,7 +64,8 @@ SIGNATURES = {
                             _vp]),
     "b2048_td_phase_a": (_int, [_int, _vp, _vp, _GP, _f32, _vp, _vp, _RP, _vp, _vp, _vp, _vp, _i64, _vp]),
     "b2048_td_run": (_int, [_int, _vp, _vp, _vp, _GP, _f32, _int, _int, _vp, _vp, _vp, _sz, _vp]),
-    "b2048_delta_apply": (_int, [_vp, _vp, _vp, _vp, _i64, _vp]),
+    "b2048_delta_pack": (_int, [_vp, _vp, _i64, _vp]),
+    "b2048_delta_apply": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp]),
 }
 
 _lib = None

@@ -203,33 +203,20 @@ def run_td(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     importlib.import_module("2048_b200")
     from game2048 import cabi, engine
+    from game2048 import parallel
     ctx = engine.Context.get()
     n, B, S = args.n, args.games, args.lock_steps
     mode = mode_bits(cabi, args)
     w_host = torch.from_numpy(seeded_weights(n)).pin_memory()
-    wd = w_host.to(ctx.device)
-    games = engine.GameBatch(B, seed=0, id_stride=B * world, ctx=ctx).init(first_id=rank * B)
-    delta = ctx.zeros(wd.numel(), torch.float32) if world > 1 else None
-    w_sync = wd.clone() if world > 1 else None
-    dsum = ctx.zeros(wd.numel(), torch.float32) if world > 1 else None
-    tr = engine.TDTrainer(ctx, n, wd, games, args.alpha, mode, delta=delta)
+    # games sharded by global slot id (rank r owns slots [r*B, (r+1)*B)), weights replicated, per-rank deltas
+    # allreduced over NCCL every --sync-every lock-steps (2048_b200/game2048/parallel.py)
+    st = parallel.ShardedTrainer(n, w_host.numpy(), B, args.alpha, mode, seed=0, sync_every=args.sync_every)
+    tr, wd, games = st.trainer, st.w, st.trainer.games
     flush = ctx.zeros(64 << 20, torch.int32)                     # 256 MiB > 126 MB L2
     launches_per_lockstep = {0: 2, 2: 3, 1: 3, 3: 3}.get(mode, None)
 
     def step():
-        if world == 1:
-            tr.run(S)
-            return
-        done = 0
-        while done < S:
-            k = min(args.sync_every, S - done)
-            tr.run(k)
-            dsum.copy_(delta)
-            dist.all_reduce(dsum, op=dist.ReduceOp.AVG)          # NCCL over NVLink: model averaging of the deltas
-            check = ctx.lib.b2048_delta_apply(engine.dptr(wd), engine.dptr(w_sync), engine.dptr(delta),
-                                              engine.dptr(dsum), wd.numel(), engine.cur_stream())
-            cabi.check(check, "delta_apply")
-            done += k
+        st.run(S)
 
     def barrier():
         torch.cuda.synchronize()

@@ -218,10 +218,17 @@ int b2048_td_run(int n, float *weights, float *delta, const uint32_t *lut, const
                  int mode, int steps, uint64_t *upd_board, float *upd_dw, void *work, size_t work_bytes,
                  b2048_stream_t stream);
 
-/* multi-GPU weight sync: after allreduce(sum) of every rank's delta into delta_sum,
- * w_sync += delta_sum; weights = w_sync; delta = 0  -- one fused pass, replicas end bit-identical. */
-int b2048_delta_apply(float *weights, float *w_sync, float *delta, const float *delta_sum, int64_t count,
-                      b2048_stream_t stream);
+/* multi-GPU weight sync.  Every rank accumulates its increments in `delta` (while also applying
+ * them locally); every K lock-steps:
+ *   b2048_delta_pack:  packed[0..count) = delta, packed[count..2count) = (delta != 0) ? 1 : 0
+ *   allreduce(sum) of packed over the ranks (NCCL, in place)
+ *   b2048_delta_apply: w_sync[k] += sum_k / max(1, contributors_k);  weights[k] = w_sync[k];  delta[k] = 0
+ * i.e. the per-key-mean rule applied across ranks (a key only one rank touched keeps its full update; a key
+ * every rank touched gets their mean) -- one fused pass, replicas end bit-identical.  contributors == NULL
+ * gives the plain sum  w_sync += delta_sum. */
+int b2048_delta_pack(const float *delta, float *packed, int64_t count, b2048_stream_t stream);
+int b2048_delta_apply(float *weights, float *w_sync, float *delta, const float *delta_sum, const float *contributors,
+                      int64_t count, b2048_stream_t stream);
 
 #ifdef __cplusplus
 }

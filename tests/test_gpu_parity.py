@@ -429,9 +429,19 @@ def test_finished_game_log_and_delta_apply(eng, orc, fx):
     dsum = delta.clone() * 2
     check = w0 + 2 * delta.cpu().numpy()
     cabi.check(ctx.lib.b2048_delta_apply(engine.dptr(wd), engine.dptr(w_sync), engine.dptr(delta), engine.dptr(dsum),
-                                         len(w0), engine.cur_stream()))
+                                         None, len(w0), engine.cur_stream()))
     assert np.array_equal(wd.cpu().numpy(), check) and np.array_equal(w_sync.cpu().numpy(), check)
     assert not delta.any().item()
+    # per-key mean over contributing ranks: pack -> (sum over 3 fake ranks) -> apply
+    d1 = torch.zeros(1000, device=ctx.device); d1[::3] = 0.5
+    packed = ctx.zeros(2000, torch.float32)
+    cabi.check(ctx.lib.b2048_delta_pack(engine.dptr(d1), engine.dptr(packed), 1000, engine.cur_stream()))
+    assert torch.equal(packed[:1000], d1) and torch.equal(packed[1000:], (d1 != 0).float())
+    tot = packed * 3                                              # three identical ranks
+    w1, ws = ctx.zeros(1000, torch.float32), ctx.zeros(1000, torch.float32)
+    cabi.check(ctx.lib.b2048_delta_apply(engine.dptr(w1), engine.dptr(ws), engine.dptr(d1), engine.dptr(tot),
+                                         engine.dptr(tot[1000:]), 1000, engine.cur_stream()))
+    assert torch.equal(w1[::3], torch.full_like(w1[::3], 0.5)) and not w1[1::3].any().item() and not d1.any().item()
 
 
 def test_argument_errors(eng):
