@@ -379,7 +379,9 @@ __host__ __device__ __forceinline__ void for_each_feature(Fn &&f)
 }
 
 // QAgent.evaluate (r_learning.py:202-203): sequential float32 sum in table order, from 0.
-template <int N>
+// COHERENT: read through L2 (ld.global.cg) instead of the non-coherent L1 path -- required inside the
+// persistent training kernel, where other SMs update the tables between lock-steps of the same launch.
+template <int N, bool COHERENT = false>
 __device__ __forceinline__ float evaluate(const float *__restrict__ w, uint64_t b)
 {
     constexpr int F = num_feat(N);
@@ -387,7 +389,8 @@ __device__ __forceinline__ float evaluate(const float *__restrict__ w, uint64_t 
     float v[F];
     for_each_feature<N>([&](auto I) {
         constexpr int i = decltype(I)::value;
-        v[i] = __ldg(w + table_offset(N, i) + feat_index<N, i>(b, y));   // all gathers in flight first
+        const float *p = w + table_offset(N, i) + feat_index<N, i>(b, y);
+        v[i] = COHERENT ? __ldcg(p) : __ldg(p);                           // all gathers in flight first
     });
     float acc = 0.0f;
 #pragma unroll

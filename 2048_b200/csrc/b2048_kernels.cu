@@ -306,30 +306,20 @@ __device__ __forceinline__ void accumulate_key(bool exact, void *__restrict__ ac
     if (old == 0) touched[atomicAdd(&ctrl->count, 1u)] = uint32_t(k);
 }
 
-template <int N, bool EXACT, bool MEAN, bool DIRECT>
-__global__ void __launch_bounds__(128)
-td_accum_kernel(float *__restrict__ w, float *__restrict__ delta, void *__restrict__ acc, uint32_t *__restrict__ cnt,
-                uint32_t *__restrict__ touched, UpdCtrl *__restrict__ ctrl, const uint64_t *__restrict__ boards,
-                const float *__restrict__ dw, int64_t m)
+// The contributions of one (entry, image) lane for the tables i with i % CH == chunk (CH = 1: all tables).
+// Must be called by all 32 lanes of a warp with a warp-uniform `chunk`; lanes 8k..8k+7 hold the 8 images of
+// one entry.
+template <int N, bool EXACT, bool MEAN, bool DIRECT, int CH>
+__device__ __forceinline__ void accum_features(float *__restrict__ w, float *__restrict__ delta, void *__restrict__ acc,
+                                               uint32_t *__restrict__ cnt, uint32_t *__restrict__ touched,
+                                               uint32_t *__restrict__ count, uint64_t b, float d, bool live, int s,
+                                               int lane, int chunk, int64_t replica_off)
 {
-    const int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
-    const int64_t j = t >> 3;
-    const int s = int(t & 7), lane = threadIdx.x & 31;
-    const bool on = j < m;
-    const float d = on ? __ldg(dw + j) : NAN;
-    const bool live = on && (EXACT ? isfinite(d) : !isnan(d));
-    if (!__any_sync(FULL, live)) return;
-    const uint64_t b = d4_image(on ? __ldg(boards + j) : 0, s);
     const uint64_t y = (N == 6) ? clamp13(b) : 0;
     const long long q = (EXACT && live) ? quantize(d) : 0;
-    constexpr int64_t NW = table_offset(N, num_feat(N));
-    constexpr int F = num_feat(N);
-    const int64_t replica_off = int64_t(blockIdx.x % acc_replicas(NW)) * NW;
-    // pass 1: all atomics of the thread are issued back to back (17-33 independent L2 round trips in flight);
-    // pass 2 consumes the returned counts.  A single loop would serialise one round trip per table.
-    uint32_t old[F], key[F];
     for_each_feature<N>([&](auto I) {
         constexpr int i = decltype(I)::value;
+        if (CH > 1 && (i % CH) != chunk) return;
         const uint32_t f = feat_index<N, i>(b, y);
         const uint32_t k = uint32_t(table_offset(N, i)) + f;
         uint32_t first = 1;
@@ -357,8 +347,6 @@ td_accum_kernel(float *__restrict__ w, float *__restrict__ delta, void *__restri
             }
             if (!MEAN) nf = 1;
         }
-        old[i] = 1;
-        key[i] = k;
         if (live && lane == __ffs(peers) - 1) {
             if (DIRECT) {
                 atomicAdd(w + k, fsum);
@@ -368,18 +356,63 @@ td_accum_kernel(float *__restrict__ w, float *__restrict__ delta, void *__restri
                     atomicAdd(reinterpret_cast<unsigned long long *>(acc) + replica_off + k, (unsigned long long)qsum);
                 else
                     atomicAdd(reinterpret_cast<float *>(acc) + replica_off + k, fsum);
-                old[i] = atomicAdd(cnt + k, nf);
+                if (atomicAdd(cnt + k, nf) == 0) touched[atomicAdd(count, 1u)] = k;
             }
         }
     });
-    if (!DIRECT) {
-#pragma unroll
-        for (int i = 0; i < F; i++)
-            if (old[i] == 0) touched[atomicAdd(&ctrl->count, 1u)] = key[i];
-    }
+}
+
+template <int N, bool EXACT, bool MEAN, bool DIRECT>
+__global__ void __launch_bounds__(128)
+td_accum_kernel(float *__restrict__ w, float *__restrict__ delta, void *__restrict__ acc, uint32_t *__restrict__ cnt,
+                uint32_t *__restrict__ touched, UpdCtrl *__restrict__ ctrl, const uint64_t *__restrict__ boards,
+                const float *__restrict__ dw, int64_t m)
+{
+    const int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    const int64_t j = t >> 3;
+    const int s = int(t & 7), lane = threadIdx.x & 31;
+    const bool on = j < m;
+    const float d = on ? __ldg(dw + j) : NAN;
+    const bool live = on && (EXACT ? isfinite(d) : !isnan(d));
+    if (!__any_sync(FULL, live)) return;
+    const uint64_t b = d4_image(on ? __ldg(boards + j) : 0, s);
+    constexpr int64_t NW = table_offset(N, num_feat(N));
+    const int64_t replica_off = int64_t(blockIdx.x % acc_replicas(NW)) * NW;
+    accum_features<N, EXACT, MEAN, DIRECT, 1>(w, delta, acc, cnt, touched, ctrl ? &ctrl->count : nullptr, b, d, live, s,
+                                              lane, 0, replica_off);
 }
 
 // ---- apply pass: one thread per touched key, plain loads/stores --------------------------------
+template <bool EXACT, bool MEAN, bool COHERENT>
+__device__ __forceinline__ void apply_key(float *__restrict__ w, float *__restrict__ delta, void *__restrict__ acc,
+                                          uint32_t *__restrict__ cnt, uint32_t k, int64_t nw, int R)
+{
+    const uint32_t c = COHERENT ? __ldcg(cnt + k) : cnt[k];
+    float u;
+    if (EXACT) {
+        long long *a = reinterpret_cast<long long *>(acc) + k;
+        long long qs = 0;
+        for (int r = 0; r < R; r++) {
+            long long v = COHERENT ? __ldcg(a + r * nw) : a[r * nw];
+            if (v) { qs += v; a[r * nw] = 0; }
+        }
+        double x = double(qs) / FIX_SCALE;
+        if (MEAN) x = x / double(c);
+        u = __double2float_rn(x);
+    } else {
+        float *a = reinterpret_cast<float *>(acc) + k;
+        float fs = 0.0f;
+        for (int r = 0; r < R; r++) {
+            float v = COHERENT ? __ldcg(a + r * nw) : a[r * nw];
+            if (v != 0.0f) { fs += v; a[r * nw] = 0.0f; }
+        }
+        u = MEAN ? __fdiv_rn(fs, float(c)) : fs;
+    }
+    cnt[k] = 0;
+    w[k] = __fadd_rn(COHERENT ? __ldcg(w + k) : w[k], u);
+    if (delta) delta[k] = __fadd_rn(COHERENT ? __ldcg(delta + k) : delta[k], u);
+}
+
 template <bool EXACT, bool MEAN>
 __global__ void __launch_bounds__(256)
 td_apply_kernel(float *__restrict__ w, float *__restrict__ delta, void *__restrict__ acc, uint32_t *__restrict__ cnt,
@@ -387,33 +420,8 @@ td_apply_kernel(float *__restrict__ w, float *__restrict__ delta, void *__restri
 {
     const int R = acc_replicas(nw);
     const uint32_t count = *reinterpret_cast<volatile uint32_t *>(&ctrl->count);
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < count; t += gridDim.x * blockDim.x) {
-        const uint32_t k = touched[t];
-        const uint32_t c = cnt[k];
-        float u;
-        if (EXACT) {
-            long long *a = reinterpret_cast<long long *>(acc) + k;
-            long long qs = 0;
-            for (int r = 0; r < R; r++) {
-                long long v = a[r * nw];
-                if (v) { qs += v; a[r * nw] = 0; }
-            }
-            double x = double(qs) / FIX_SCALE;
-            if (MEAN) x = x / double(c);
-            u = __double2float_rn(x);
-        } else {
-            float *a = reinterpret_cast<float *>(acc) + k;
-            float fs = 0.0f;
-            for (int r = 0; r < R; r++) {
-                float v = a[r * nw];
-                if (v != 0.0f) { fs += v; a[r * nw] = 0.0f; }
-            }
-            u = MEAN ? __fdiv_rn(fs, float(c)) : fs;
-        }
-        cnt[k] = 0;
-        w[k] = __fadd_rn(w[k], u);
-        if (delta) delta[k] = __fadd_rn(delta[k], u);
-    }
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < count; t += gridDim.x * blockDim.x)
+        apply_key<EXACT, MEAN, false>(w, delta, acc, cnt, touched[t], nw, R);
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
@@ -640,7 +648,7 @@ __device__ __forceinline__ void log_finished(const b2048_games_t &g, uint64_t id
 
 // One afterstate per lane (lane d of a 4-lane group = direction d), value by n-tuple gather, then a
 // width-4 shuffle argmax with the reference's tie rule (strict '>' scanning d = 0..3: lowest d wins).
-template <int N>
+template <int N, bool COHERENT = false>
 __device__ __forceinline__ void best_move(const float *__restrict__ w, const LutGlobal &L, uint64_t board, int d,
                                           bool run, uint64_t &best_after, uint32_t &best_gain, float &best_value,
                                           int &best_dir, uint32_t &best_flags, uint32_t &n_valid)
@@ -648,7 +656,7 @@ __device__ __forceinline__ void best_move(const float *__restrict__ w, const Lut
     uint32_t gain = 0, fl = 0;
     uint64_t after = move_dir(L, board, d, gain, fl);
     const bool valid = run && (fl & 1u);
-    float v = valid ? evaluate<N>(w, after) : -INFINITY;
+    float v = valid ? evaluate<N, COHERENT>(w, after) : -INFINITY;
     // a direction that would create 2^16 is kept valid here; the caller stops the game if it wins
     float bv = v;
     int bd = valid ? d : 4;                           // invalid lanes never win ties
@@ -756,20 +764,33 @@ greedy_play_kernel(const float *__restrict__ w, const uint32_t *__restrict__ lut
     warp_add_counter(g.counters + B2048_CTR_ACTIVE, (in && d == 0 && !(flags & B2048_F_DONE)) ? 1u : 0u);
 }
 
-// TD lock-step, phase A (see b2048.h).  4 lanes per slot.
-template <int N>
-__global__ void __launch_bounds__(128)
-td_phase_a_kernel(const float *__restrict__ w, const uint32_t *__restrict__ lut, b2048_games_t g, float alpha,
-                  uint64_t *__restrict__ upd_board, float *__restrict__ upd_dw, b2048_replay_t rp, int has_replay,
-                  int8_t *__restrict__ trace_dir, float *__restrict__ trace_value, float *__restrict__ trace_dw,
-                  uint16_t *__restrict__ trace_spawn, int64_t trace_len)
+// TD lock-step, phase A (see b2048.h).  4 lanes per slot (lane d = direction d); all 32 lanes of a warp must
+// call this together (width-4 shuffles inside).
+struct StepCounters {
+    uint32_t moves = 0, evals = 0, upd = 0, fin = 0, score = 0, msum = 0, ovf = 0;
+};
+
+__device__ __forceinline__ void flush_counters(uint64_t *counters, StepCounters &c)
+{
+    warp_add_counter(counters + B2048_CTR_MOVES, c.moves);
+    warp_add_counter(counters + B2048_CTR_EVALS, c.evals);
+    warp_add_counter(counters + B2048_CTR_UPDATES, c.upd);
+    warp_add_counter(counters + B2048_CTR_FINISHED, c.fin);
+    warp_add_counter(counters + B2048_CTR_SCORE_SUM, c.score);
+    warp_add_counter(counters + B2048_CTR_MOVES_SUM, c.msum);
+    warp_add_counter(counters + B2048_CTR_OVERFLOW, c.ovf);
+    c = StepCounters{};
+}
+
+template <int N, bool COHERENT>
+__device__ __forceinline__ void phase_a_slot(const float *__restrict__ w, const LutGlobal &L, const b2048_games_t &g,
+                                             float alpha, int64_t slot, int d, bool in, uint64_t *__restrict__ upd_board,
+                                             float *__restrict__ upd_dw, const b2048_replay_t &rp, int has_replay,
+                                             int8_t *__restrict__ trace_dir, float *__restrict__ trace_value,
+                                             float *__restrict__ trace_dw, uint16_t *__restrict__ trace_spawn,
+                                             int64_t trace_len, StepCounters &c)
 {
     constexpr int F = num_feat(N);
-    const int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
-    const int64_t slot = t >> 2;
-    const int d = int(t & 3);
-    const bool in = slot < g.B;
-    LutGlobal L{lut};
     uint64_t board = in ? g.board[slot] : 0;
     uint32_t score = in ? g.score[slot] : 0;
     uint32_t odo = in ? g.moves[slot] : 0;
@@ -786,10 +807,9 @@ td_phase_a_kernel(const float *__restrict__ w, const uint32_t *__restrict__ lut,
     uint32_t bg, bf, nv;
     float bv;
     int bd;
-    best_move<N>(w, L, board, d, run && !over, ba, bg, bv, bd, bf, nv);
+    best_move<N, COHERENT>(w, L, board, d, run && !over, ba, bg, bv, bd, bf, nv);
     float dw = NAN;
     uint64_t ub = 0;
-    uint32_t c_moves = 0, c_evals = 0, c_upd = 0, c_fin = 0, c_score = 0, c_msum = 0, c_ovf = 0;
     if (run) {
         const bool finished = over || (bf & 2u);
         if (finished) {
@@ -798,8 +818,8 @@ td_phase_a_kernel(const float *__restrict__ w, const uint32_t *__restrict__ lut,
                 ub = state;
             }
             if (d == 0) {
-                c_fin++; c_score += score; c_msum += odo;
-                if (!over) c_ovf++;
+                c.fin++; c.score += score; c.msum += odo;
+                if (!over) c.ovf++;
                 atomicAdd(g.tile_hist + (over ? max_tile(board) : 16), 1u);
                 log_finished(g, id, score, odo, over ? uint32_t(max_tile(board)) : 16u, board);
                 if (trace_dir && int64_t(odo) < trace_len) {
@@ -824,7 +844,7 @@ td_phase_a_kernel(const float *__restrict__ w, const uint32_t *__restrict__ lut,
                 ub = state;
             }
             if (d == 0) {
-                c_moves++; c_evals += nv;
+                c.moves++; c.evals += nv;
                 if (trace_dir && int64_t(odo) < trace_len) {
                     trace_dir[slot * trace_len + odo] = int8_t(bd);
                     if (trace_value) trace_value[slot * trace_len + odo] = bv;
@@ -851,7 +871,7 @@ td_phase_a_kernel(const float *__restrict__ w, const uint32_t *__restrict__ lut,
             }
             if (d == 0 && trace_spawn && int64_t(odo) <= trace_len) trace_spawn[slot * trace_len + odo - 1] = uint16_t(sp);
         }
-        if (d == 0 && !isnan(dw)) c_upd++;
+        if (d == 0 && !isnan(dw)) c.upd++;
     }
     if (in && d == 0) {
         upd_board[slot] = ub;
@@ -866,13 +886,22 @@ td_phase_a_kernel(const float *__restrict__ w, const uint32_t *__restrict__ lut,
             g.flags[slot] = uint8_t(flags);
         }
     }
-    warp_add_counter(g.counters + B2048_CTR_MOVES, c_moves);
-    warp_add_counter(g.counters + B2048_CTR_EVALS, c_evals);
-    warp_add_counter(g.counters + B2048_CTR_UPDATES, c_upd);
-    warp_add_counter(g.counters + B2048_CTR_FINISHED, c_fin);
-    warp_add_counter(g.counters + B2048_CTR_SCORE_SUM, c_score);
-    warp_add_counter(g.counters + B2048_CTR_MOVES_SUM, c_msum);
-    warp_add_counter(g.counters + B2048_CTR_OVERFLOW, c_ovf);
+}
+
+template <int N>
+__global__ void __launch_bounds__(128)
+td_phase_a_kernel(const float *__restrict__ w, const uint32_t *__restrict__ lut, b2048_games_t g, float alpha,
+                  uint64_t *__restrict__ upd_board, float *__restrict__ upd_dw, b2048_replay_t rp, int has_replay,
+                  int8_t *__restrict__ trace_dir, float *__restrict__ trace_value, float *__restrict__ trace_dw,
+                  uint16_t *__restrict__ trace_spawn, int64_t trace_len)
+{
+    const int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    const int64_t slot = t >> 2;
+    LutGlobal L{lut};
+    StepCounters c;
+    phase_a_slot<N, false>(w, L, g, alpha, slot, int(t & 3), slot < g.B, upd_board, upd_dw, rp, has_replay, trace_dir,
+                           trace_value, trace_dw, trace_spawn, trace_len, c);
+    flush_counters(g.counters, c);
 }
 
 __global__ void delta_pack_kernel(const float *__restrict__ delta, float *__restrict__ packed, int64_t count)
