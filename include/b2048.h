@@ -123,8 +123,9 @@ int b2048_evaluate(int n, const float *weights, const uint64_t *boards, int64_t 
  *                            many games hit the same key in one lock-step; == SUM at m == 1
  * Within a warp, lanes that hit the same key are merged before the atomic (hot keys such as empty rows).
  * delta (may be NULL) receives the same increments as weights (multi-GPU delta buffer).
- * work: b2048_td_update_workspace(n, m, mode) bytes (0 for ATOMIC|SUM); zero it once before the first
- * call; every call leaves it ready for the next one (accumulators and counters back at zero). */
+ * work: b2048_td_update_workspace(n, m, mode) bytes (b2048_td_update itself ignores it for ATOMIC|SUM; the
+ * fused loops below always need it); zero it once before the first call; every call leaves it ready for the
+ * next one (accumulators and counters back at zero). */
 #define B2048_UPD_ATOMIC 0
 #define B2048_UPD_DETERMINISTIC 1
 #define B2048_UPD_SUM 0
@@ -213,7 +214,12 @@ int b2048_td_phase_a(int n, const float *weights, const uint32_t *lut, const b20
                      uint64_t *upd_board, float *upd_dw, const b2048_replay_t *replay, int8_t *trace_dir,
                      float *trace_value, float *trace_dw, uint16_t *trace_spawn, int64_t trace_len,
                      b2048_stream_t stream);
-/* `steps` lock-steps enqueued back to back (no host work in between). */
+/* `steps` lock-steps with no host work in between.  Default: ONE cooperative launch of a persistent kernel
+ * (every CTA owns a fixed range of slots; phase A and the accumulation run back to back, a grid barrier, the
+ * CTA applies the keys it touched first, a grid barrier) -- same results as `steps` calls of b2048_td_step
+ * (bit-identical in the DETERMINISTIC modes).  mode | B2048_RUN_STEPWISE (or B2048_UPD_SORTED, or a device
+ * without cooperative launch) enqueues b2048_td_step `steps` times instead (3 launches per lock-step). */
+#define B2048_RUN_STEPWISE 8
 int b2048_td_run(int n, float *weights, float *delta, const uint32_t *lut, const b2048_games_t *g, float alpha,
                  int mode, int steps, uint64_t *upd_board, float *upd_dw, void *work, size_t work_bytes,
                  b2048_stream_t stream);
