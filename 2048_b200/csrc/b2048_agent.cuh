@@ -527,22 +527,56 @@ __device__ __forceinline__ void flush_counters(uint64_t *counters, StepCounters 
     c = StepCounters{};
 }
 
+// one game slot in registers (b2048_games_t, structure of arrays in memory)
+struct SlotState {
+    uint64_t board, id, state;
+    uint32_t score, odo, flags;
+    float old_label;
+};
+
+__device__ __forceinline__ SlotState slot_load(const b2048_games_t &g, int64_t slot, bool in)
+{
+    SlotState s;
+    s.board = in ? g.board[slot] : 0;
+    s.score = in ? g.score[slot] : 0;
+    s.odo = in ? g.moves[slot] : 0;
+    s.flags = in ? g.flags[slot] : B2048_F_DONE;
+    s.id = in ? g.game_id[slot] : 0;
+    s.state = in ? g.state[slot] : 0;
+    s.old_label = in ? g.old_label[slot] : 0.0f;
+    return s;
+}
+
+__device__ __forceinline__ void slot_store(const b2048_games_t &g, int64_t slot, const SlotState &s)
+{
+    g.board[slot] = s.board;
+    g.score[slot] = s.score;
+    g.moves[slot] = s.odo;
+    g.game_id[slot] = s.id;
+    g.state[slot] = s.state;
+    g.old_label[slot] = s.old_label;
+    g.flags[slot] = uint8_t(s.flags);
+}
+
+// One lock-step of one slot (QAgent.episode body, r_learning.py:228-249) on the register copy `s`: returns true if
+// the slot was live (its state changed); (ub, dw) = the TD update to apply (dw = NaN: none).  4 lanes per slot
+// (lane d = direction d); all 32 lanes of a warp must call this together (width-4 shuffles inside).
 template <int N, bool COHERENT>
-__device__ __forceinline__ void phase_a_slot(const float *__restrict__ w, const LutGlobal &L, const b2048_games_t &g,
-                                             float alpha, int64_t slot, int d, bool in, uint64_t *__restrict__ upd_board,
-                                             float *__restrict__ upd_dw, const b2048_replay_t &rp, int has_replay,
-                                             int8_t *__restrict__ trace_dir, float *__restrict__ trace_value,
-                                             float *__restrict__ trace_dw, uint16_t *__restrict__ trace_spawn,
-                                             int64_t trace_len, StepCounters &c)
+__device__ __forceinline__ bool phase_a_compute(const float *__restrict__ w, const LutGlobal &L, const b2048_games_t &g,
+                                                float alpha, int64_t slot, int d, bool in, SlotState &s, uint64_t &ub,
+                                                float &dw, const b2048_replay_t &rp, int has_replay,
+                                                int8_t *__restrict__ trace_dir, float *__restrict__ trace_value,
+                                                float *__restrict__ trace_dw, uint16_t *__restrict__ trace_spawn,
+                                                int64_t trace_len, StepCounters &c)
 {
     constexpr int F = num_feat(N);
-    uint64_t board = in ? g.board[slot] : 0;
-    uint32_t score = in ? g.score[slot] : 0;
-    uint32_t odo = in ? g.moves[slot] : 0;
-    uint32_t flags = in ? g.flags[slot] : B2048_F_DONE;
-    uint64_t id = in ? g.game_id[slot] : 0;
-    uint64_t state = in ? g.state[slot] : 0;
-    float old_label = in ? g.old_label[slot] : 0.0f;
+    uint64_t board = s.board;
+    uint32_t score = s.score;
+    uint32_t odo = s.odo;
+    uint32_t flags = s.flags;
+    uint64_t id = s.id;
+    uint64_t state = s.state;
+    float old_label = s.old_label;
     bool run = in && !(flags & B2048_F_DONE);
     if (run && has_replay && !game_over(board)) {
         if (int64_t(odo) >= rp.len || __ldg(rp.tile + slot * rp.len + odo) == 0) run = false;   // spawns exhausted
@@ -553,8 +587,8 @@ __device__ __forceinline__ void phase_a_slot(const float *__restrict__ w, const 
     float bv;
     int bd;
     best_move<N, COHERENT>(w, L, board, d, run && !over, ba, bg, bv, bd, bf, nv);
-    float dw = NAN;
-    uint64_t ub = 0;
+    dw = NAN;
+    ub = 0;
     if (run) {
         const bool finished = over || (bf & 2u);
         if (finished) {
@@ -618,18 +652,35 @@ __device__ __forceinline__ void phase_a_slot(const float *__restrict__ w, const 
         }
         if (d == 0 && !isnan(dw)) c.upd++;
     }
+    if (run) {
+        s.board = board;
+        s.score = score;
+        s.odo = odo;
+        s.id = id;
+        s.state = state;
+        s.old_label = old_label;
+        s.flags = flags;
+    }
+    return run;
+}
+
+template <int N, bool COHERENT>
+__device__ __forceinline__ void phase_a_slot(const float *__restrict__ w, const LutGlobal &L, const b2048_games_t &g,
+                                             float alpha, int64_t slot, int d, bool in, uint64_t *__restrict__ upd_board,
+                                             float *__restrict__ upd_dw, const b2048_replay_t &rp, int has_replay,
+                                             int8_t *__restrict__ trace_dir, float *__restrict__ trace_value,
+                                             float *__restrict__ trace_dw, uint16_t *__restrict__ trace_spawn,
+                                             int64_t trace_len, StepCounters &c)
+{
+    SlotState s = slot_load(g, slot, in);
+    uint64_t ub;
+    float dw;
+    const bool run = phase_a_compute<N, COHERENT>(w, L, g, alpha, slot, d, in, s, ub, dw, rp, has_replay, trace_dir,
+                                                  trace_value, trace_dw, trace_spawn, trace_len, c);
     if (in && d == 0) {
         upd_board[slot] = ub;
         upd_dw[slot] = dw;
-        if (run) {
-            g.board[slot] = board;
-            g.score[slot] = score;
-            g.moves[slot] = odo;
-            g.game_id[slot] = id;
-            g.state[slot] = state;
-            g.old_label[slot] = old_label;
-            g.flags[slot] = uint8_t(flags);
-        }
+        if (run) slot_store(g, slot, s);
     }
 }
 
@@ -653,227 +704,441 @@ td_phase_a_kernel(const float *__restrict__ w, const uint32_t *__restrict__ lut,
 // persistent lock-step trainer: `steps` lock-steps of QAgent.episode for all slots in ONE cooperative
 // launch (b2048_td_run).  The stepwise path costs 3 launches (~4.5 us each) plus three pipeline
 // fill/drain phases per lock-step; here every CTA owns a fixed range of game slots and runs
-//     phase A (own slots, weights read through L2)                 -> upd_board / upd_dw
-//     phase B (own entries: 8 images x F tables, warp-merged)      -> acc / cnt (+ the CTA's own key list)
+//     phase A  own slots, weights read through L2 (ld.cg)             -> upd_board / upd_dw
+//     phase B  own entries, one thread per (entry, table): 8 D4 images -> accumulators
+//     flush    the CTA's shared-memory table of small-exponent keys   -> dense global hot table (RED)
 //     ---- grid barrier ----
-//     apply   (the keys this CTA touched FIRST: w += S [/ G], accumulators back to zero)
+//     apply    the keys this CTA touched FIRST + its slice of the hot table: w += S [/ G], accumulators := 0
 //     ---- grid barrier ----
-// Phase B writes only the accumulators, never w, so no barrier is needed between A and B of different
-// CTAs; the DIRECT variant (atomic + sum rule, increments straight into w) needs one there instead.
-// One accumulator copy (no replicas): the first-touch test must see every contribution to a key.
-//   float modes   acc = float2[nw] {sum, count}: ONE returning ATOMG.ADD.F32x2 per merged contribution
+// Phase B writes only accumulators, never w, so no barrier is needed between A and B of different CTAs; the
+// DIRECT variant (atomic + sum rule, increments straight into w) needs one there instead.
+//
+// Accumulators (one copy, no replicas: the first-touch test must see every contribution to a key):
+//   float modes   acc = float2[nw] {sum, count}: ONE returning ATOMG.ADD.F32x2 per contribution
 //   exact modes   acc = int64[nw] (RED.64) + cnt = u32[nw] (returning ATOMG), as in the stepwise path
-// A contribution that finds count == 0 appends its key to the CTA-private list (shared-memory cursor), so the
-// apply phase has no global counter, no global list and no atomics.
+// The contribution that finds count == 0 appends its key to the CTA-private list (shared-memory cursor), so
+// the apply phase needs no global counter, no global list and no atomics.
+//
+// Hot keys.  Keys whose cells are all <= 3 (empty, 2, 4, 8) take ~30 % of all contributions and include every
+// really hot address (thousands of games per lock-step on "empty row").  They are dense: 4^cells per table.
+// Each CTA accumulates them in shared memory, then adds its non-zero entries to a dense global hot table with
+// fire-and-forget REDs (<= one per CTA and key), which the apply phase scans in slices.  No first-touch
+// bookkeeping, no same-address pile-up in L2.
+//
+// No warp-level key matching here: __match_any_sync costs ~12 cycles per distinct value (380 cycles for 32
+// distinct keys, measured, profiles/microbench/warpops.cu) and serialises per SM sub-partition.  A thread owns
+// one table of one entry and compares its own 8 image keys in registers (an entry counts once per key in G).
 // ------------------------------------------------------------------------------------------------
 
-__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t *p)
+__device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t *p)
 {
     uint32_t v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 
-// all CTAs of a cooperative launch; `target` is the CTA's running arrival total (thread 0 only)
+// All CTAs of a cooperative launch; `target` is the CTA's running arrival total (thread 0 only).
+// Arrival = red.release.gpu (MEMBAR.ALL.GPU + RED: the CTA's earlier writes and atomics are performed first);
+// the wait polls with relaxed loads and does NOT invalidate L1 (no CCTL.IVALL): everything another CTA may have
+// written is read with ld.cg (L2) afterwards, while the row LUT and the CTA's own game slots stay L1-resident.
 __device__ __forceinline__ void grid_barrier(uint32_t *bar, uint32_t &target)
 {
     __syncthreads();
     if (threadIdx.x == 0) {
         target += gridDim.x;
-        __threadfence();                              // release: the CTA's writes and atomics before the arrival
-        atomicAdd(bar, 1u);
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
         // a wait of 2^25 polls (seconds) can only be a lost CTA: trap instead of hanging the device
         uint32_t polls = 0;
-        while (ld_acquire_gpu(bar) < target)
+        while (ld_relaxed_gpu(bar) < target)
             if (++polls > (1u << 25)) __trap();
     }
     __syncthreads();
 }
 
-template <int N, int I, int CH, class Fn>
-__device__ __forceinline__ void for_each_feature_strided(Fn &&f)
+// ---- dense small-exponent key space --------------------------------------------------------------
+__host__ __device__ constexpr int small_tables(int n) { return n == 6 ? 21 : num_feat(n); }   // base-16 tables only
+__host__ __device__ constexpr int tuple_cells(int n, int i) { return n <= 3 ? n : i < 17 ? 4 : i < 21 ? 5 : 6; }
+__host__ __device__ constexpr int small_offset(int n, int i)            // first dense index of table i
 {
-    if constexpr (I < num_feat(N)) {
-        f(std::integral_constant<int, I>{});
-        for_each_feature_strided<N, I + CH, CH>(f);
-    }
+    int o = 0;
+    for (int k = 0; k < i && k < small_tables(n); k++) o += 1 << (2 * tuple_cells(n, k));
+    return o;
+}
+__host__ __device__ constexpr int small_count(int n) { return small_offset(n, small_tables(n)); }
+
+template <int N>
+__device__ __forceinline__ uint32_t table_offset_rt(int i)
+{
+    if (N <= 4) return uint32_t(i) * uint32_t(table_size(N, 0));
+    return i <= 17 ? uint32_t(i) * 65536u : i <= 21 ? 17u * 65536u + uint32_t(i - 17) * 1048576u
+                                                    : 17u * 65536u + 4u * 1048576u + uint32_t(i - 21) * 7529536u;
 }
 
-struct AccumTarget {
+template <int N>
+__device__ __forceinline__ int small_offset_rt(int i)
+{
+    if (N <= 4) return i << (2 * N);
+    return i <= 17 ? i << 8 : (17 << 8) + ((i - 17) << 10);
+}
+
+// dense index -> weight index (inverse of the compaction in phase B)
+template <int N>
+__device__ __forceinline__ uint32_t small_to_key(int dense)
+{
+    int tab, compact, cells;
+    if (N <= 4) { tab = dense >> (2 * N); compact = dense & ((1 << (2 * N)) - 1); cells = N; }
+    else if (dense < (17 << 8)) { tab = dense >> 8; compact = dense & 255; cells = 4; }
+    else { tab = 17 + ((dense - (17 << 8)) >> 10); compact = (dense - (17 << 8)) & 1023; cells = 5; }
+    uint32_t idx = 0;
+#pragma unroll
+    for (int k = 0; k < 5; k++)
+        if (k < cells) idx |= uint32_t((compact >> (2 * k)) & 3) << (4 * k);
+    return table_offset_rt<N>(tab) + idx;
+}
+
+struct PersistBuffers {
     float *w, *delta;
-    void *acc;
-    uint32_t *cnt;
-    uint32_t *list;         // this CTA's key list (global memory segment)
-    uint32_t *cursor;       // its length (shared memory)
+    void *acc;              // float2[nw] | int64[nw]
+    uint32_t *cnt;          // exact modes: u32[nw]
+    uint32_t *lists;        // per-CTA key lists, list_cap keys each
+    void *hot;              // float2[NS] | int64[NS] followed by u32[NS]
+    int64_t list_cap;
 };
 
-// Tables i = C, C+CH, ... of the 4 entries x 8 images held by one warp (lanes 8e..8e+7 = entry e).
-// One __match_any_sync per table yields everything the merge needs: the lanes sharing the key (any entry,
-// any image), hence per entry e the number of its images on the key (c_e) -- sum = sum_e c_e * dw_e,
-// distinct entries G = #{e : c_e > 0} -- and the leader lane that issues the atomic.
-// Pass 1 issues every atomic of the chunk back to back; pass 2 consumes the returned counts (a single loop
-// would expose one L2 round trip per table).
-template <int N, bool EXACT, bool MEAN, bool DIRECT, int C, int CH>
-__device__ __forceinline__ void accum_chunk(const AccumTarget &t, uint64_t b, const float (&de)[4],
-                                            const long long (&qe)[4], bool live, int lane)
+template <bool EXACT, bool MEAN>
+__device__ __forceinline__ float update_value(long long q, float fs, float c)
 {
-    constexpr int F = num_feat(N);
-    constexpr int P = (F - C + CH - 1) / CH;
-    const uint64_t y = (N == 6) ? clamp13(b) : 0;
-    uint32_t key[P];
-    float oldf[P];
-    uint32_t oldu[P];
-    for_each_feature_strided<N, C, CH>([&](auto I) {
-        constexpr int i = decltype(I)::value;
-        constexpr int p = (i - C) / CH;
-        const uint32_t k = uint32_t(table_offset(N, i)) + feat_index<N, i>(b, y);
-        const uint32_t peers = __match_any_sync(FULL, live ? k : ~uint32_t(lane));
-        const int c0 = __popc(peers & 0x000000FFu), c1 = __popc(peers & 0x0000FF00u);
-        const int c2 = __popc(peers & 0x00FF0000u), c3 = __popc(peers & 0xFF000000u);
-        key[p] = k;
-        oldf[p] = 1.0f;
-        oldu[p] = 1u;
-        if (live && lane == __ffs(peers) - 1) {
-            const uint32_t nf = MEAN ? uint32_t((c0 != 0) + (c1 != 0) + (c2 != 0) + (c3 != 0)) : 1u;
-            if (EXACT) {
-                const long long qs = c0 * qe[0] + c1 * qe[1] + c2 * qe[2] + c3 * qe[3];
-                atomicAdd(reinterpret_cast<unsigned long long *>(t.acc) + k, (unsigned long long)qs);
-                oldu[p] = atomicAdd(t.cnt + k, nf);
-            } else {
-                float fs = c0 ? float(c0) * de[0] : 0.0f;
-                if (c1) fs += float(c1) * de[1];
-                if (c2) fs += float(c2) * de[2];
-                if (c3) fs += float(c3) * de[3];
-                if (DIRECT) {
-                    atomicAdd(t.w + k, fs);
-                    if (t.delta) atomicAdd(t.delta + k, fs);
-                } else {
-                    oldf[p] = atomicAdd(reinterpret_cast<float2 *>(t.acc) + k, make_float2(fs, float(nf))).y;
-                }
-            }
-        }
-    });
-    if (DIRECT) return;
-    uint32_t first = 0, total = 0;                    // bit p: this lane saw count 0 -> >0 on key[p]
-    uint32_t before[P];
-#pragma unroll
-    for (int p = 0; p < P; p++) {
-        const bool f = EXACT ? (oldu[p] == 0u) : (oldf[p] == 0.0f);
-        const uint32_t m = __ballot_sync(FULL, f);
-        first |= uint32_t(f) << p;
-        before[p] = total + __popc(m & ((1u << lane) - 1u));
-        total += __popc(m);
+    if (EXACT) {
+        double x = double(q) / FIX_SCALE;
+        if (MEAN) x = x / double(c);
+        return __double2float_rn(x);
     }
-    if (total) {                                      // warp-uniform
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(t.cursor, total);
-        base = __shfl_sync(FULL, base, 0);
-#pragma unroll
-        for (int p = 0; p < P; p++)
-            if ((first >> p) & 1u) t.list[base + before[p]] = key[p];
-    }
+    return MEAN ? __fdiv_rn(fs, c) : fs;
 }
 
-template <bool EXACT, bool MEAN>
-__device__ __forceinline__ void apply_key_single(float *__restrict__ w, float *__restrict__ delta, void *__restrict__ acc,
-                                                 uint32_t *__restrict__ cnt, uint32_t k)
+__device__ __forceinline__ void add_weight(float *__restrict__ w, float *__restrict__ delta, uint32_t k, float u)
 {
-    float u;
-    if (EXACT) {
-        long long *a = reinterpret_cast<long long *>(acc) + k;
-        const long long qs = __ldcg(a);
-        const uint32_t c = __ldcg(cnt + k);
-        double x = double(qs) / FIX_SCALE;
-        if (MEAN) x = x / double(c);
-        u = __double2float_rn(x);
-        __stcg(a, 0LL);
-        __stcg(cnt + k, 0u);
-    } else {
-        float2 *a = reinterpret_cast<float2 *>(acc) + k;
-        const float2 v = __ldcg(a);
-        u = MEAN ? __fdiv_rn(v.x, v.y) : v.x;
-        __stcg(a, make_float2(0.0f, 0.0f));
-    }
     __stcg(w + k, __fadd_rn(__ldcg(w + k), u));
     if (delta) __stcg(delta + k, __fadd_rn(__ldcg(delta + k), u));
 }
 
+constexpr int PERSIST_TILE = 32;           // FAST path: at most this many slots per CTA
 
-template <int N, bool EXACT, bool MEAN, bool DIRECT, int CH>
+// FAST: the CTA's slots fit one phase-B round (slots <= 512 / F) -- the headline shape, 4,096 games on 148 SMs.
+// Game state then lives in registers for the whole launch, phase A hands (dw, 8 D4 images) to phase B through
+// shared memory, and a thread keeps the keys it touched first (and the small-key entries it made non-zero) in
+// registers across the barrier and applies / flushes them itself: no lists, no cursors, no global round trip
+// except the weight gathers and the atomics.  Otherwise slots are processed in rounds through the b2048_td_step
+// staging arrays and per-CTA key lists in global memory.
+template <int N, bool EXACT, bool MEAN, bool DIRECT, bool FAST>
 __global__ void __launch_bounds__(PERSIST_THREADS, 1)
-td_persist_kernel(float *w, float *delta, void *acc, uint32_t *cnt, uint32_t *lists, PersistCtrl *ctrl,
-                  const uint32_t *__restrict__ lut, b2048_games_t g, float alpha, int steps, uint64_t *upd_board,
-                  float *upd_dw, int spc, int64_t list_cap, long long *tlog)
+td_persist_kernel(PersistBuffers pb, PersistCtrl *ctrl, const uint32_t *__restrict__ lut, b2048_games_t g, float alpha,
+                  int steps, uint64_t *upd_board, float *upd_dw, int spc, long long *tlog)
 {
-    // tlog (debug, B2048_PERSIST_TLOG): clock64 at the 6 phase boundaries of the last 16 steps, per CTA
-    __shared__ uint32_t s_cursor;
+    // tlog (debug, B2048_PERSIST_TLOG): clock64 at the phase boundaries of the last 16 steps, per CTA
+    constexpr int F = num_feat(N);
+    constexpr int NS = small_count(N);
+    constexpr int MAXC = N;                                // cells of the widest tuple
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // small-key accumulators: sums (float | int64), counts (u32), dirty list (u16 dense indices)
+    float *s_sum = reinterpret_cast<float *>(smem_raw);
+    unsigned long long *s_q = reinterpret_cast<unsigned long long *>(smem_raw);
+    uint32_t *s_cnt = reinterpret_cast<uint32_t *>(smem_raw + size_t(NS) * (EXACT ? 8 : 4));
+    uint16_t *s_dirty = reinterpret_cast<uint16_t *>(smem_raw + size_t(NS) * (EXACT ? 12 : 8));
+    __shared__ uint32_t s_cursor, s_ndirty;
+    __shared__ uint64_t s_img[FAST ? PERSIST_TILE * 8 : 1];
+    __shared__ float s_dw[FAST ? PERSIST_TILE : 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int64_t slot0 = int64_t(blockIdx.x) * spc;
     const int nslots = int(g.B - slot0 < spc ? (g.B - slot0 > 0 ? g.B - slot0 : 0) : spc);
-    const AccumTarget tgt{w, delta, acc, cnt, lists + int64_t(blockIdx.x) * list_cap, &s_cursor};
+    uint32_t *list = pb.lists + int64_t(blockIdx.x) * pb.list_cap;     // generic path only
+    float2 *acc2 = reinterpret_cast<float2 *>(pb.acc);
+    unsigned long long *accq = reinterpret_cast<unsigned long long *>(pb.acc);
+    float2 *hot2 = reinterpret_cast<float2 *>(pb.hot);
+    unsigned long long *hotq = reinterpret_cast<unsigned long long *>(pb.hot);
+    uint32_t *hotc = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(pb.hot) + size_t(NS) * 8);
     const b2048_replay_t no_replay{nullptr, nullptr, 0};
     LutGlobal L{lut};
     StepCounters c;
     uint32_t bar_target = 0;
+
+    for (int q = threadIdx.x; q < NS; q += blockDim.x) {
+        if (EXACT) s_q[q] = 0; else s_sum[q] = 0.0f;
+        s_cnt[q] = 0;
+    }
+    // phase A role (FAST): lane d of slot threadIdx.x / 4, state in registers
+    const int a_slot = int(threadIdx.x) >> 2, a_dir = int(threadIdx.x) & 3;
+    const bool a_warp = FAST && warp * 8 < nslots, a_in = FAST && a_slot < nslots;
+    SlotState st{};
+    bool st_dirty = false;
+    if (FAST) st = slot_load(g, slot0 + a_slot, a_in);
+    // phase B role: table `tab` of entries erow, erow + EPR, ...
+    const int EPR = blockDim.x / F;
+    const bool worker = int(threadIdx.x) < EPR * F;
+    const int tab = int(threadIdx.x) % F, erow = int(threadIdx.x) / F;
+    const FeatSpec spec = feat_spec(N, tab);
+    int sh[MAXC];
+#pragma unroll
+    for (int k = 0; k < MAXC; k++) sh[k] = 4 * (15 - spec.cell[k < spec.ncell ? k : 0]);
+    const int ncell = spec.ncell;
+    const bool base14 = spec.base == 14;
+    const uint32_t key_off = table_offset_rt<N>(tab);
+    const int dense_off = small_offset_rt<N>(tab);
+    const uint32_t big_mask = base14 ? 0u : (0xCCCCCCu & ((1u << (4 * ncell)) - 1u));   // any cell > 3
+    const int rounds = (nslots + EPR - 1) / EPR;
+    __syncthreads();
+
     for (int step = 0; step < steps; step++) {
-        if (threadIdx.x == 0) s_cursor = 0;
+        if (threadIdx.x == 0) { s_cursor = 0; s_ndirty = 0; }
         long long *tl = (tlog && threadIdx.x == 0 && step >= steps - 16) ?
-                        tlog + (int64_t(blockIdx.x) * 16 + (step - (steps - 16))) * 6 : nullptr;
+                        tlog + (int64_t(blockIdx.x) * 16 + (step - (steps - 16))) * 8 : nullptr;
         if (tl) tl[0] = clock64();
         // ---- phase A: 4 lanes per slot, 8 slots per warp
-        for (int base = warp * 8; base < nslots; base += nwarps * 8) {
-            const int ls = base + (lane >> 2);
-            phase_a_slot<N, true>(w, L, g, alpha, slot0 + ls, lane & 3, ls < nslots, upd_board, upd_dw, no_replay, 0,
-                                  nullptr, nullptr, nullptr, nullptr, 0, c);
+        if (FAST) {
+            if (a_warp) {
+                uint64_t ub;
+                float dw;
+                st_dirty |= phase_a_compute<N, true>(pb.w, L, g, alpha, slot0 + a_slot, a_dir, a_in, st, ub, dw, no_replay, 0,
+                                                     nullptr, nullptr, nullptr, nullptr, 0, c);
+                if (a_in) {                                   // lane d stages images d and 4 + d (d4_image order)
+                    uint64_t im = (a_dir & 1) ? flip_h(ub) : ub;
+                    if (a_dir & 2) im = flip_v(im);
+                    s_img[a_slot * 8 + a_dir] = im;
+                    s_img[a_slot * 8 + 4 + a_dir] = transpose(im);
+                    if (a_dir == 0) s_dw[a_slot] = dw;
+                }
+            }
+        } else {
+            for (int base = warp * 8; base < nslots; base += nwarps * 8) {
+                const int ls = base + (lane >> 2);
+                phase_a_slot<N, true>(pb.w, L, g, alpha, slot0 + ls, lane & 3, ls < nslots, upd_board, upd_dw, no_replay,
+                                      0, nullptr, nullptr, nullptr, nullptr, 0, c);
+            }
         }
         if (DIRECT) grid_barrier(&ctrl->bar, bar_target);     // every slot has read W_t before anyone adds to it
         else __syncthreads();
         if (tl) tl[1] = clock64();
-        // ---- phase B: 8 lanes per entry, 4 entries per warp, CH table chunks per entry group
-        const int ngroups = (nslots + 3) >> 2;
-        for (int it = warp; it < ngroups * CH; it += nwarps) {
-            const int eg = it % ngroups, chunk = it / ngroups;
-            const int le = eg * 4 + (lane >> 3);
-            const bool on = le < nslots;
-            const float d = on ? __ldcg(upd_dw + slot0 + le) : NAN;
-            const bool live = on && (EXACT ? isfinite(d) : !isnan(d));
-            if (!__any_sync(FULL, live)) continue;
-            const uint64_t b = d4_image(on ? __ldcg(upd_board + slot0 + le) : 0, lane & 7);
-            float de[4];
-            long long qe[4];
-            const long long q = (EXACT && live) ? quantize(d) : 0;
+        // ---- phase B: one thread per (entry, table); image s: key, duplicate test against the lower images,
+        //      atomic -- issued image by image so that the key arithmetic overlaps the atomics in flight
+        uint32_t idx[8], first = 0, dirty = 0;                // FAST: survive the barrier (the thread applies them)
+        for (int r = 0; r < rounds; r++) {
+            const int e = r * EPR + erow;
+            const bool on = worker && e < nslots;
+            float d = NAN;
+            uint64_t img[8];
+            if (FAST) {
+                if (on) d = s_dw[e];
 #pragma unroll
-            for (int e = 0; e < 4; e++) {
-                de[e] = __shfl_sync(FULL, d, 8 * e);
-                qe[e] = EXACT ? (long long)shfl64(uint64_t(q), 8 * e, 32) : 0;
-            }
-            if constexpr (CH == 1) {
-                accum_chunk<N, EXACT, MEAN, DIRECT, 0, 1>(tgt, b, de, qe, live, lane);
-            } else if constexpr (CH == 2) {
-                if (chunk == 0) accum_chunk<N, EXACT, MEAN, DIRECT, 0, 2>(tgt, b, de, qe, live, lane);
-                else            accum_chunk<N, EXACT, MEAN, DIRECT, 1, 2>(tgt, b, de, qe, live, lane);
+                for (int s = 0; s < 8; s++) img[s] = on ? s_img[e * 8 + s] : 0;
+                if (base14) {
+#pragma unroll
+                    for (int s = 0; s < 8; s++) img[s] = clamp13(img[s]);
+                }
             } else {
-                static_assert(CH == 4, "table chunks: 1, 2 or 4");
-                if (chunk == 0)      accum_chunk<N, EXACT, MEAN, DIRECT, 0, 4>(tgt, b, de, qe, live, lane);
-                else if (chunk == 1) accum_chunk<N, EXACT, MEAN, DIRECT, 1, 4>(tgt, b, de, qe, live, lane);
-                else if (chunk == 2) accum_chunk<N, EXACT, MEAN, DIRECT, 2, 4>(tgt, b, de, qe, live, lane);
-                else                 accum_chunk<N, EXACT, MEAN, DIRECT, 3, 4>(tgt, b, de, qe, live, lane);
+                if (on) d = __ldcg(upd_dw + slot0 + e);
+                const uint64_t b0 = on ? __ldcg(reinterpret_cast<const unsigned long long *>(upd_board) + slot0 + e) : 0;
+                img[0] = base14 ? clamp13(b0) : b0;
+                img[1] = flip_h(img[0]);
+                img[2] = flip_v(img[0]);
+                img[3] = flip_v(img[1]);
+#pragma unroll
+                for (int s = 0; s < 4; s++) img[4 + s] = transpose(img[s]);
+            }
+            const bool live = on && (EXACT ? isfinite(d) : !isnan(d));
+            const long long qd = (EXACT && live) ? quantize(d) : 0;
+            float oldf[8];
+            uint32_t oldu[8];
+            dirty = 0;
+#pragma unroll
+            for (int s = 0; s < 8; s++) {
+                uint32_t v = 0;
+#pragma unroll
+                for (int k = 0; k < MAXC; k++)
+                    if (k < ncell) {
+                        const uint32_t cell = uint32_t(img[s] >> sh[k]) & 15u;
+                        v = base14 ? v * 14u + cell : (v << 4) | cell;
+                    }
+                idx[s] = v;
+                bool ld = true;                               // no lower image of this entry has the same key
+#pragma unroll
+                for (int o = 0; o < s; o++) ld &= idx[o] != v;
+                oldf[s] = 1.0f;
+                oldu[s] = 1u;
+                if (!live) continue;
+                if ((v & big_mask) == 0 && !base14) {         // small-exponent key: shared memory
+                    uint32_t cmp = 0;
+#pragma unroll
+                    for (int k = 0; k < MAXC; k++) cmp |= ((v >> (4 * k)) & 3u) << (2 * k);
+                    const int di = dense_off + int(cmp);
+                    if (EXACT) atomicAdd(s_q + di, (unsigned long long)qd); else atomicAdd(s_sum + di, d);
+                    if (ld && atomicAdd(s_cnt + di, 1u) == 0u) dirty |= 1u << s;
+                } else {
+                    const uint32_t k = key_off + v;
+                    if (DIRECT) {
+                        atomicAdd(pb.w + k, d);
+                        if (pb.delta) atomicAdd(pb.delta + k, d);
+                    } else if (EXACT) {
+                        atomicAdd(accq + k, (unsigned long long)qd);
+                        if (ld) oldu[s] = atomicAdd(pb.cnt + k, 1u);
+                    } else if (ld) {
+                        oldf[s] = atomicAdd(acc2 + k, make_float2(d, 1.0f)).y;
+                    } else {
+                        atomicAdd(acc2 + k, make_float2(d, 0.0f));
+                    }
+                }
+            }
+            first = 0;
+            if (!DIRECT) {
+#pragma unroll
+                for (int s = 0; s < 8; s++) first |= uint32_t(EXACT ? (oldu[s] == 0u) : (oldf[s] == 0.0f)) << s;
+            }
+            if (!FAST) {
+                // first touches -> the CTA's key list; first small-key touches -> its dirty list (one warp scan)
+                const uint32_t mine = __popc(first) | (__popc(dirty) << 16);
+                uint32_t incl = mine;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t up = __shfl_up_sync(FULL, incl, o);
+                    if (lane >= o) incl += up;
+                }
+                const uint32_t total = __shfl_sync(FULL, incl, 31);
+                if (total) {                                  // warp-uniform
+                    uint32_t base_f = 0, base_d = 0;
+                    if (lane == 0) {
+                        if (total & 0xFFFFu) base_f = atomicAdd(&s_cursor, total & 0xFFFFu);
+                        if (total >> 16) base_d = atomicAdd(&s_ndirty, total >> 16);
+                    }
+                    uint32_t pf = __shfl_sync(FULL, base_f, 0) + ((incl - mine) & 0xFFFFu);
+                    uint32_t pd = __shfl_sync(FULL, base_d, 0) + ((incl - mine) >> 16);
+#pragma unroll
+                    for (int s = 0; s < 8; s++) {
+                        if ((first >> s) & 1u) list[pf++] = key_off + idx[s];
+                        if ((dirty >> s) & 1u) {
+                            uint32_t cmp = 0;
+#pragma unroll
+                            for (int k = 0; k < MAXC; k++) cmp |= ((idx[s] >> (4 * k)) & 3u) << (2 * k);
+                            s_dirty[pd++] = uint16_t(dense_off + int(cmp));
+                        }
+                    }
+                }
             }
         }
         __syncthreads();
         if (tl) tl[2] = clock64();
-        grid_barrier(&ctrl->bar, bar_target);                 // every contribution of the step has landed
+        // ---- flush the dirty entries of the small-key table (and zero them for the next step): FAST, the thread
+        //      that made an entry non-zero flushes it; otherwise from the CTA's dirty list
+        {
+            auto flush_entry = [&](int q) {
+                const uint32_t cv = s_cnt[q];
+                s_cnt[q] = 0;
+                if (DIRECT) {
+                    const uint32_t k = small_to_key<N>(q);
+                    atomicAdd(pb.w + k, s_sum[q]);
+                    if (pb.delta) atomicAdd(pb.delta + k, s_sum[q]);
+                    s_sum[q] = 0.0f;
+                } else if (EXACT) {
+                    atomicAdd(hotq + q, s_q[q]);
+                    atomicAdd(hotc + q, cv);
+                    s_q[q] = 0;
+                } else {
+                    atomicAdd(hot2 + q, make_float2(s_sum[q], float(cv)));
+                    s_sum[q] = 0.0f;
+                }
+            };
+            if (FAST) {
+#pragma unroll
+                for (int s = 0; s < 8; s++)
+                    if ((dirty >> s) & 1u) {
+                        uint32_t cmp = 0;
+#pragma unroll
+                        for (int k = 0; k < MAXC; k++) cmp |= ((idx[s] >> (4 * k)) & 3u) << (2 * k);
+                        flush_entry(dense_off + int(cmp));
+                    }
+            } else {
+                const uint32_t nd = s_ndirty;
+                for (uint32_t t = threadIdx.x; t < nd; t += blockDim.x) flush_entry(s_dirty[t]);
+            }
+        }
         if (tl) tl[3] = clock64();
+        grid_barrier(&ctrl->bar, bar_target);                 // every contribution of the step has landed
+        if (tl) tl[4] = clock64();
         if (!DIRECT) {
-            const uint32_t mine = s_cursor;
-            for (uint32_t q = threadIdx.x; q < mine; q += blockDim.x)
-                apply_key_single<EXACT, MEAN>(w, delta, acc, cnt, __ldcg(tgt.list + q));
+            auto apply_key = [&](uint32_t k) {
+                float u;
+                if (EXACT) {
+                    const long long qs = (long long)__ldcg(accq + k);
+                    const uint32_t cv = __ldcg(pb.cnt + k);
+                    u = update_value<true, MEAN>(qs, 0.0f, float(cv));
+                    __stcg(accq + k, 0ULL);
+                    __stcg(pb.cnt + k, 0u);
+                } else {
+                    const float2 v = __ldcg(acc2 + k);
+                    u = update_value<false, MEAN>(0, v.x, v.y);
+                    __stcg(acc2 + k, make_float2(0.0f, 0.0f));
+                }
+                add_weight(pb.w, pb.delta, k, u);
+            };
+            if (FAST) {
+                // the keys this thread touched first (registers): every load first, then the arithmetic and the
+                // stores -- one L2 round trip for up to 8 keys instead of one per key
+                float2 av[8];
+                long long aq[8];
+                uint32_t ac[8];
+                float wv[8], dv[8];
+#pragma unroll
+                for (int s = 0; s < 8; s++) {
+                    const uint32_t k = key_off + idx[s];
+                    if ((first >> s) & 1u) {
+                        if (EXACT) { aq[s] = (long long)__ldcg(accq + k); ac[s] = __ldcg(pb.cnt + k); }
+                        else av[s] = __ldcg(acc2 + k);
+                        wv[s] = __ldcg(pb.w + k);
+                        if (pb.delta) dv[s] = __ldcg(pb.delta + k);
+                    }
+                }
+#pragma unroll
+                for (int s = 0; s < 8; s++) {
+                    const uint32_t k = key_off + idx[s];
+                    if ((first >> s) & 1u) {
+                        float u;
+                        if (EXACT) {
+                            u = update_value<true, MEAN>(aq[s], 0.0f, float(ac[s]));
+                            __stcg(accq + k, 0ULL);
+                            __stcg(pb.cnt + k, 0u);
+                        } else {
+                            u = update_value<false, MEAN>(0, av[s].x, av[s].y);
+                            __stcg(acc2 + k, make_float2(0.0f, 0.0f));
+                        }
+                        __stcg(pb.w + k, __fadd_rn(wv[s], u));
+                        if (pb.delta) __stcg(pb.delta + k, __fadd_rn(dv[s], u));
+                    }
+                }
+            } else {
+                const uint32_t mine = s_cursor;
+                for (uint32_t q = threadIdx.x; q < mine; q += blockDim.x) apply_key(__ldcg(list + q));
+            }
+            for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < NS; q += gridDim.x * blockDim.x) {
+                float u;
+                if (EXACT) {
+                    const uint32_t cv = __ldcg(hotc + q);
+                    if (!cv) continue;
+                    u = update_value<true, MEAN>((long long)__ldcg(hotq + q), 0.0f, float(cv));
+                    __stcg(hotq + q, 0ULL);
+                    __stcg(hotc + q, 0u);
+                } else {
+                    const float2 v = __ldcg(hot2 + q);
+                    if (v.y == 0.0f) continue;
+                    u = update_value<false, MEAN>(0, v.x, v.y);
+                    __stcg(hot2 + q, make_float2(0.0f, 0.0f));
+                }
+                add_weight(pb.w, pb.delta, small_to_key<N>(q), u);
+            }
             __syncthreads();
-            if (tl) tl[4] = clock64();
+            if (tl) tl[5] = clock64();
             grid_barrier(&ctrl->bar, bar_target);             // W_{t+1} complete
         }
-        if (tl) tl[5] = clock64();
+        if (tl) tl[6] = clock64();
     }
+    if (FAST && a_in && a_dir == 0 && st_dirty) slot_store(g, slot0 + a_slot, st);
     flush_counters(g.counters, c);
     if (threadIdx.x == 0) {
         __threadfence();
@@ -960,25 +1225,35 @@ int td_update_impl(float *weights, float *delta, const uint64_t *boards, const f
 }
 
 // ---- persistent trainer launch ---------------------------------------------------------------------
-template <int N, bool EXACT, bool MEAN, bool DIRECT, int CH>
+template <int N, bool EXACT, bool MEAN, bool DIRECT, bool FAST>
 int launch_persist(int grid, cudaStream_t st, void **args)
 {
-    auto kern = td_persist_kernel<N, EXACT, MEAN, DIRECT, CH>;
+    auto kern = td_persist_kernel<N, EXACT, MEAN, DIRECT, FAST>;
+    const int smem = small_count(N) * (EXACT ? 14 : 10);           // sums, counts, dirty list
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return int(e);
+        attr_set[dev] = true;
+    }
     int occ = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, PERSIST_THREADS, 0);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, PERSIST_THREADS, smem);
     if (e != cudaSuccess) return int(e);
     if (occ < 1 || grid > occ * sm_count()) return B2048_ENOTSUP;       // all CTAs must be co-resident
-    e = cudaLaunchCooperativeKernel(reinterpret_cast<void *>(kern), dim3(unsigned(grid)), dim3(PERSIST_THREADS), args, 0, st);
+    e = cudaLaunchCooperativeKernel(reinterpret_cast<void *>(kern), dim3(unsigned(grid)), dim3(PERSIST_THREADS), args,
+                                    size_t(smem), st);
     return e == cudaSuccess ? 0 : int(e);
 }
 
-template <int N, int CH>
+template <int N, bool FAST>
 int launch_persist_mode(bool det, bool mean, int grid, cudaStream_t st, void **args)
 {
-    if (!det && !mean) return launch_persist<N, false, false, true, CH>(grid, st, args);
-    if (!det) return launch_persist<N, false, true, false, CH>(grid, st, args);
-    if (mean) return launch_persist<N, true, true, false, CH>(grid, st, args);
-    return launch_persist<N, true, false, false, CH>(grid, st, args);
+    if (!det && !mean) return launch_persist<N, false, false, true, FAST>(grid, st, args);
+    if (!det) return launch_persist<N, false, true, false, FAST>(grid, st, args);
+    if (mean) return launch_persist<N, true, true, false, FAST>(grid, st, args);
+    return launch_persist<N, true, false, false, FAST>(grid, st, args);
 }
 
 template <int N>
@@ -990,57 +1265,47 @@ int td_run_persistent(float *weights, float *delta, const uint32_t *lut, const b
     const int64_t B = g->B;
     WorkLayout L = work_layout(N, B, mode | B2048_UPD_MEAN);       // DIRECT uses only the control block
     if (!work || work_bytes < work_layout(N, B, mode).total) return B2048_EWORK;
-    // one CTA per SM (tunable): slots per CTA = a multiple of 4 (one warp = 4 entries in phase B)
-    int max_grid = sm_count() * env_int("B2048_PERSIST_CTAS_PER_SM", 1);
+    // one CTA per SM: slots per CTA rounded up to a multiple of 4
+    int max_grid = sm_count();
     if (max_grid > PERSIST_MAX_GRID) max_grid = PERSIST_MAX_GRID;
-    int64_t spc = cdiv(cdiv(B, max_grid), 4) * 4;
+    const int64_t spc = cdiv(cdiv(B, max_grid), 4) * 4;
     const int grid = int(cdiv(B, spc));
-    const int groups = int(spc / 4);
-    // table chunks: spread the entry groups of a CTA over its 16 warps
-    int ch = env_int("B2048_PERSIST_CHUNKS", 0);
-    if (ch != 1 && ch != 2 && ch != 4) ch = groups * 4 <= PERSIST_THREADS / 32 ? 4 : groups * 2 <= PERSIST_THREADS / 32 ? 2 : 1;
-    if (N == 6 && ch == 1) ch = 2;                                 // bounds the registers of a chunk
     unsigned char *base = reinterpret_cast<unsigned char *>(work);
-    void *acc = base + L.acc;
-    uint32_t *cnt = reinterpret_cast<uint32_t *>(base + L.cnt), *lists = reinterpret_cast<uint32_t *>(base + L.lists);
+    PersistBuffers pb{weights, delta, base + L.acc, reinterpret_cast<uint32_t *>(base + L.cnt),
+                      reinterpret_cast<uint32_t *>(base + L.lists), base + L.hot, spc * 8 * num_feat(N)};
     PersistCtrl *ctrl = reinterpret_cast<PersistCtrl *>(base + L.ctrl);
     b2048_games_t games = *g;
     int spc_i = int(spc);
-    int64_t list_cap = spc * 8 * num_feat(N);
     long long *tlog = nullptr;
     const char *tlog_path = getenv("B2048_PERSIST_TLOG");          // debug: per-phase clocks -> text file
     if (tlog_path && *tlog_path && steps >= 16) {
-        if (cudaMalloc(&tlog, size_t(grid) * 16 * 6 * sizeof(long long)) != cudaSuccess) tlog = nullptr;
-        else cudaMemsetAsync(tlog, 0, size_t(grid) * 16 * 6 * sizeof(long long), st);
+        if (cudaMalloc(&tlog, size_t(grid) * 16 * 8 * sizeof(long long)) != cudaSuccess) tlog = nullptr;
+        else cudaMemsetAsync(tlog, 0, size_t(grid) * 16 * 8 * sizeof(long long), st);
     }
-    void *args[] = {&weights, &delta, &acc, &cnt, &lists, &ctrl, &lut, &games, &alpha, &steps, &upd_board, &upd_dw,
-                    &spc_i, &list_cap, &tlog};
-    int rc = B2048_EINVAL;
-    switch (ch) {
-    case 1: rc = launch_persist_mode<N, 1>(det, mean, grid, st, args); break;
-    case 2: rc = launch_persist_mode<N, 2>(det, mean, grid, st, args); break;
-    default: rc = launch_persist_mode<N, 4>(det, mean, grid, st, args); break;
-    }
+    void *args[] = {&pb, &ctrl, &lut, &games, &alpha, &steps, &upd_board, &upd_dw, &spc_i, &tlog};
+    // FAST: one phase-B round per lock-step, state in registers, staging and key list in shared memory
+    const bool fast = spc <= PERSIST_THREADS / num_feat(N) && spc <= PERSIST_TILE && !env_int("B2048_PERSIST_GENERIC", 0);
+    const int rc = fast ? launch_persist_mode<N, true>(det, mean, grid, st, args)
+                        : launch_persist_mode<N, false>(det, mean, grid, st, args);
     if (tlog) {
-        std::vector<long long> h(size_t(grid) * 16 * 6);
+        std::vector<long long> h(size_t(grid) * 16 * 8);
         cudaStreamSynchronize(st);
         cudaMemcpy(h.data(), tlog, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
         cudaFree(tlog);
         if (FILE *f = fopen(tlog_path, "a")) {
-            fprintf(f, "# grid %d spc %d ch %d mode %d n %d steps %d: per CTA, per step: A B bar1 apply bar2 (cycles)\n", grid,
-                    spc_i, ch, mode, N, steps);
+            fprintf(f, "# grid %d spc %d mode %d n %d steps %d: per CTA, per step: A B flush bar1 apply bar2 (cycles)\n", grid,
+                    spc_i, mode, N, steps);
             for (int c = 0; c < grid; c++)
                 for (int q = 0; q < 16; q++) {
-                    const long long *t = &h[(size_t(c) * 16 + q) * 6];
-                    fprintf(f, "%d %d %lld %lld %lld %lld %lld\n", c, q, t[1] - t[0], t[2] - t[1], t[3] - t[2],
-                            t[4] ? t[4] - t[3] : 0, t[4] ? t[5] - t[4] : 0);
+                    const long long *t = &h[(size_t(c) * 16 + q) * 8];
+                    fprintf(f, "%d %d %lld %lld %lld %lld %lld %lld\n", c, q, t[1] - t[0], t[2] - t[1], t[3] - t[2],
+                            t[4] - t[3], t[5] ? t[5] - t[4] : 0, t[5] ? t[6] - t[5] : 0);
                 }
             fclose(f);
         }
     }
     return rc;
 }
-
 
 template <int N>
 int features_impl(const uint64_t *boards, int64_t m, int32_t *feat, cudaStream_t st)

@@ -85,7 +85,7 @@ inline int key_bits(int n)
 struct WorkLayout {
     int64_t M, nw;      // contributions, weights
     int nblocks;        // sort tiles
-    size_t acc, cnt, touched, ctrl, keys_a, keys_b, vals_a, vals_b, hist, lists, total;
+    size_t acc, cnt, touched, ctrl, keys_a, keys_b, vals_a, vals_b, hist, lists, hot, total;
 };
 
 inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
@@ -115,6 +115,7 @@ inline WorkLayout work_layout(int n, int64_t m, int mode)
     }
     // persistent trainer: per-CTA key lists, entries_per_CTA * 8F keys each (PERSIST_MAX_GRID CTAs at most)
     L.lists = o; o += align256(size_t(m + 4 * PERSIST_MAX_GRID) * 8 * num_feat(n) * 4);
+    L.hot = o; o += align256(size_t(17 * 256 + 4 * 1024) * 12);      // dense table of the small-exponent keys
     L.total = o;
     return L;
 }

@@ -392,6 +392,32 @@ def test_td_lockstep_deterministic_bit_exact(eng, orc, fx, n, B):
         assert np.array_equal(ha["tile_hist"], ls.hist)
 
 
+@pytest.mark.parametrize("n,B,steps,force_generic", [(4, 64, 200, True), (5, 5000, 60, False), (6, 700, 40, False),
+                                                     (2, 4096, 50, False)])
+def test_td_persistent_paths_bit_exact(eng, orc, fx, monkeypatch, n, B, steps, force_generic):
+    """b2048_td_run's persistent kernel, both slot layouts (FAST: state in registers, one phase-B round; generic:
+    rounds over global staging) and the stepwise path all give the oracle's bits in the deterministic modes."""
+    ctx, engine, cabi = eng
+    if force_generic:
+        monkeypatch.setenv("B2048_PERSIST_GENERIC", "1")
+    for rule, mode, alpha in ((4, cabi.UPD_DETERMINISTIC | cabi.UPD_MEAN, 0.25),
+                              (3, cabi.UPD_DETERMINISTIC | cabi.UPD_SUM, 0.25 / B)):
+        w0 = fx.flat(fx.init_weights32(n, 41)).astype(np.float32)
+        ref_w = w0.copy()
+        ls = orc.LockStep(n, ref_w, alpha, 91, B, segmented=rule, threads=8)
+        ls.run(steps)
+        wd = ctx.to_device(w0)
+        games = engine.GameBatch(B, seed=91, ctx=ctx).init()
+        tr = engine.TDTrainer(ctx, n, wd, games, alpha, mode)
+        tr.run(steps // 3)
+        tr.run(steps - steps // 3)                                        # a second launch resumes from memory
+        h, c = games.to_host(), games.read_counters()
+        assert np.array_equal(h["board"], ls.board) and np.array_equal(h["game_id"], ls.game_id)
+        assert np.array_equal(h["old_label"], ls.old_label)
+        assert np.array_equal(wd.cpu().numpy(), ref_w)
+        assert c["updates"] == ls.n_updates and c["moves"] == ls.n_moves and c["finished"] == ls.fin[0]
+
+
 def test_td_lockstep_atomic_within_tolerance(eng, orc, fx):
     """atomic modes: same sums, unordered -> weights within 1e-5 (relative to the largest change) of the
     float64 oracle over a short stable run"""
