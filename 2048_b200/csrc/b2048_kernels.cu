@@ -470,6 +470,19 @@ int b2048_td_run(int n, float *weights, float *delta, const uint32_t *lut, const
     return 0;
 }
 
+int64_t b2048_td_run_launches(int n, int64_t B, int mode, int steps)
+{
+    if (num_feat(n) < 0 || B < 0 || steps < 0 || (mode & ~(7 | B2048_RUN_STEPWISE))) return -1;
+    if (B == 0 || steps == 0) return 0;
+    const bool stepwise = (mode & (B2048_RUN_STEPWISE | B2048_UPD_SORTED)) || env_int("B2048_STEPWISE", 0);
+    if (!stepwise && cooperative_ok()) return 1;                   // the persistent kernel
+    mode &= 7;
+    int64_t per_step = 2;                                          // phase A + direct accumulate
+    if (mode != (B2048_UPD_ATOMIC | B2048_UPD_SUM)) per_step = 3;  // + apply
+    if (mode & B2048_UPD_SORTED) per_step = 1 + 1 + 3 * ((key_bits(n) + 7) / 8) + 1 + 1;
+    return per_step * steps;
+}
+
 int b2048_delta_pack(const float *delta, float *packed, int64_t count, b2048_stream_t stream)
 {
     if (count < 0 || (count && (!delta || !packed))) return B2048_EINVAL;

@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(os.path.dirname(_HERE), "libb2048.so")
 
-UPD_ATOMIC, UPD_DETERMINISTIC, UPD_SUM, UPD_MEAN, UPD_SORTED = 0, 1, 0, 2, 4
+UPD_ATOMIC, UPD_DETERMINISTIC, UPD_SUM, UPD_MEAN, UPD_SORTED, RUN_STEPWISE = 0, 1, 0, 2, 4, 8
 F_HAVE_STATE, F_DONE, F_OVERFLOW = 1, 2, 4
 (CTR_MOVES, CTR_EVALS, CTR_UPDATES, CTR_FINISHED, CTR_SCORE_SUM, CTR_MOVES_SUM, CTR_OVERFLOW, CTR_ACTIVE,
  CTR_LOG) = range(9)
@@ -64,6 +64,7 @@ SIGNATURES = {
                             _vp]),
     "b2048_td_phase_a": (_int, [_int, _vp, _vp, _GP, _f32, _vp, _vp, _RP, _vp, _vp, _vp, _vp, _i64, _vp]),
     "b2048_td_run": (_int, [_int, _vp, _vp, _vp, _GP, _f32, _int, _int, _vp, _vp, _vp, _sz, _vp]),
+    "b2048_td_run_launches": (_i64, [_int, _i64, _int, _int]),
     "b2048_delta_pack": (_int, [_vp, _vp, _i64, _vp]),
     "b2048_delta_apply": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp]),
 }

@@ -280,13 +280,15 @@ class TDTrainer:
         self.ctx, self.n, self.w, self.games, self.alpha, self.mode = ctx, n, weights, games, float(alpha), int(mode)
         self.delta = delta
         self.upd_board, self.upd_dw = ctx.zeros(games.B, I64), ctx.zeros(games.B, F32)
-        self.work = ctx.update_workspace(n, games.B, self.mode)
+        self.work = ctx.update_workspace(n, games.B, self.mode & 7)
+        self.launches = 0                                        # kernels enqueued so far (bench: gpu_launches)
 
     def step(self, replay=None, trace=None):
         rp = C.byref(replay.c) if replay is not None else None
         td, tv, tw, ts, tl = (None, None, None, None, 0) if trace is None else trace
+        self.launches += 2 if (self.mode & 7) == 0 else 3
         check(self.ctx.lib.b2048_td_step(self.n, dptr(self.w), dptr(self.delta), dptr(self.ctx.lut),
-                                         C.byref(self.games.c), self.alpha, self.mode, dptr(self.upd_board),
+                                         C.byref(self.games.c), self.alpha, self.mode & 7, dptr(self.upd_board),
                                          dptr(self.upd_dw), dptr(self.work), self.work.numel(), rp, dptr(td), dptr(tv),
                                          dptr(tw), dptr(ts), tl, cur_stream()), "td_step")
 
@@ -298,10 +300,13 @@ class TDTrainer:
 
     def phase_b(self):
         check(self.ctx.lib.b2048_td_update(self.n, dptr(self.w), dptr(self.delta), dptr(self.upd_board),
-                                           dptr(self.upd_dw), self.games.B, self.mode, dptr(self.work),
+                                           dptr(self.upd_dw), self.games.B, self.mode & 7, dptr(self.work),
                                            self.work.numel(), cur_stream()), "td_update")
 
     def run(self, steps):
+        """`steps` lock-steps without host work in between: one persistent cooperative kernel (default), or
+        3 launches per lock-step with mode | RUN_STEPWISE"""
+        self.launches += int(self.ctx.lib.b2048_td_run_launches(self.n, self.games.B, self.mode, int(steps)))
         check(self.ctx.lib.b2048_td_run(self.n, dptr(self.w), dptr(self.delta), dptr(self.ctx.lut),
                                         C.byref(self.games.c), self.alpha, self.mode, int(steps), dptr(self.upd_board),
                                         dptr(self.upd_dw), dptr(self.work), self.work.numel(), cur_stream()), "td_run")

@@ -97,6 +97,11 @@ class ShardedTrainer:
         self.since_sync = 0
         self.syncs = 0
 
+    @property
+    def launches(self):
+        """kernels of this package enqueued so far on this rank (trainer kernels + 2 per sync)"""
+        return getattr(self.trainer, "launches", 0) + 2 * self.syncs
+
     def sync(self):
         """allreduce(sum) of [delta | touched indicator], then w_sync += sum / contributors on every rank"""
         if self.world == 1 or self.since_sync == 0:

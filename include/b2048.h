@@ -220,6 +220,8 @@ int b2048_td_phase_a(int n, const float *weights, const uint32_t *lut, const b20
  * (bit-identical in the DETERMINISTIC modes).  mode | B2048_RUN_STEPWISE (or B2048_UPD_SORTED, or a device
  * without cooperative launch) enqueues b2048_td_step `steps` times instead (3 launches per lock-step). */
 #define B2048_RUN_STEPWISE 8
+/* number of kernel launches b2048_td_run(n, B slots, mode, steps) enqueues on this device (1 = persistent) */
+int64_t b2048_td_run_launches(int n, int64_t B, int mode, int steps);
 int b2048_td_run(int n, float *weights, float *delta, const uint32_t *lut, const b2048_games_t *g, float alpha,
                  int mode, int steps, uint64_t *upd_board, float *upd_dw, void *work, size_t work_bytes,
                  b2048_stream_t stream);
