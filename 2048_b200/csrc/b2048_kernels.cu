@@ -174,19 +174,47 @@ sweep_kernel(const uint32_t *__restrict__ lut, const uint64_t *__restrict__ boar
         reinterpret_cast<uint32_t *>(scode)[q] = c;
     }
     __syncthreads();
-    LutShared L{srow, scode};
     const int64_t stride = int64_t(gridDim.x) * SWEEP_THREADS;
     for (int64_t i = blockIdx.x * int64_t(SWEEP_THREADS) + threadIdx.x; i < m; i += stride) {
-        uint64_t b = __ldg(boards + i);
+        const uint64_t b = __ldg(boards + i);
+        // every direction is "slide left" on a transformed board (pre_move = rot90 / left / rot90 back,
+        // game_logic.py:136-142): up = transpose, right = mirror, down = transpose then mirror
+        const uint64_t bt = transpose(b);
+        const uint64_t x[4] = {b, bt, flip_h(b), flip_h(bt)};
         uint64_t a[4];
         uint32_t g[4], fl = 0, ok = 0;
+        bool ovf2[2];
 #pragma unroll
         for (int d = 0; d < 4; d++) {
-            uint32_t f;
-            a[d] = move_dir(L, b, d, g[d], f);
-            fl |= (f & 1u) << d;
-            fl |= ((f >> 1) & 1u) << (4 + d);
-            ok |= uint32_t((f & 3u) == 1u) << d;
+            uint64_t out = 0;
+            uint32_t codes = 0;                                  // 8 merge exponents (2 per row), 0 = none
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const uint32_t line = uint32_t(x[d] >> (48 - 16 * r)) & 0xFFFFu;
+                out |= uint64_t(srow[line]) << (48 - 16 * r);
+                if (d < 2) codes |= uint32_t(scode[line]) << (8 * r);
+            }
+            // Merges pair up equal neighbours inside maximal runs of equal tiles, floor(L / 2) per run from either
+            // end, so the merge score and the 2^16 escape of right / down equal those of left / up: only the
+            // afterstate and the changed flag depend on the side.  (Checked exhaustively against the oracle.)
+            if (d < 2) {
+                uint32_t t = codes & (codes >> 1);
+                t &= t >> 2;
+                ovf2[d] = (t & 0x11111111u) != 0;                // a 15+15 merge
+                uint32_t sc = 0;                                 // score += 2^(e+1) per merge (game_logic.py:33)
+#pragma unroll
+                for (int q = 0; q < 8; q++) sc += (2u << ((codes >> (4 * q)) & 15u)) & ~2u;
+                g[d] = sc;
+            } else {
+                g[d] = g[d - 2];
+            }
+            const bool ovf = ovf2[d & 1];
+            const bool ch = out != x[d] || ovf;
+            if (d & 2) out = flip_h(out);
+            a[d] = (d & 1) ? transpose(out) : out;
+            fl |= uint32_t(ch) << d;
+            fl |= uint32_t(ovf) << (4 + d);
+            ok |= uint32_t(ch && !ovf) << d;
         }
         ulonglong2 *ap = reinterpret_cast<ulonglong2 *>(after + 4 * i);
         ap[0] = make_ulonglong2(a[0], a[1]);

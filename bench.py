@@ -45,6 +45,9 @@ def parse():
     p.add_argument("--sync-every", type=int, default=64, help="lock-steps between weight-delta allreduces (N>1)")
     p.add_argument("--boards", type=int, default=1 << 24, help="boards per GPU (sweep)")
     p.add_argument("--no-extras", action="store_true")
+    p.add_argument("--chunk", type=int, default=4096, help="moves per greedy launch")
+    p.add_argument("--pretrain", type=int, default=0, help="greedy: TD lock-steps (4096 games) before playing")
+    p.add_argument("--cpu-games", type=int, default=4096, help="greedy: games of the cpu_baseline sample")
     p.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     return p.parse_args()
 
@@ -386,14 +389,248 @@ def td_extras(args, ctx, engine, cabi, wd):
     return out
 
 
+# --------------------------------------------------------------------------------------------- secondary workloads
+def dist_setup():
+    import torch
+    import torch.distributed as dist
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, local
+
+
+def reduce_max_sum(vals, ctx, world):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor(vals, dtype=torch.float64, device=ctx.device)
+    if world == 1:
+        return list(vals), list(vals)
+    tmax, tsum = t.clone(), t.clone()
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+    return tmax.tolist(), tsum.tolist()
+
+
+def run_greedy(args):
+    """BASELINE configs[3] shape: greedy n-tuple play of `--games` seeded games per GPU to completion (default n=6,
+    131,072 games per GPU = 1M games on 8 GPUs), weights fixed.  One bench step = all games of the rank, played by
+    b2048_greedy_play (whole games per launch, Philox spawns keyed by GLOBAL game id, no collective)."""
+    import torch
+    import torch.distributed as dist
+    rank, world, local = dist_setup()
+    importlib.import_module("2048_b200")
+    from game2048 import cabi, engine
+    ctx = engine.Context.get()
+    n, B = args.n, args.games
+    w_host = torch.from_numpy(seeded_weights(n)).pin_memory()
+    wd = ctx.empty(w_host.numel(), torch.float32)
+    wd.copy_(w_host)
+    if args.pretrain:                                            # a briefly trained agent plays longer games
+        g0 = engine.GameBatch(4096, seed=5, ctx=ctx).init()
+        engine.TDTrainer(ctx, n, wd, g0, args.alpha, cabi.UPD_ATOMIC | cabi.UPD_MEAN).run(args.pretrain)
+        w_host.copy_(wd)
+    games = engine.GameBatch(B, seed=0, ctx=ctx)
+    flush = ctx.zeros(64 << 20, torch.int32)
+    score_host, moves_host = torch.empty(B, dtype=torch.int32).pin_memory(), torch.empty(B, dtype=torch.int32).pin_memory()
+
+    def step(e2e=False):
+        if e2e:
+            wd.copy_(w_host, non_blocking=True)
+        games.init(first_id=rank * B)
+        engine.greedy_play(ctx, n, wd, games, chunk=args.chunk)
+        if e2e:                                                  # per-game result: score, moves (+ counters)
+            score_host.copy_(games.score, non_blocking=True)
+            moves_host.copy_(games.moves, non_blocking=True)
+            return games.read_counters()
+        return None
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start(); sampler.wait_first()
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler.mark()
+    ms, moves, evals, launches = 0.0, 0, 0, 0
+    for _ in range(args.steps):
+        flush.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        step()
+        b.record()
+        torch.cuda.synchronize()
+        ms += a.elapsed_time(b)
+        c = games.read_counters()
+        moves += c["moves"]; evals += c["evals"]
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    e_ms, e_moves = 0.0, 0
+    for i in range(args.steps + 1):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        c = step(e2e=True)
+        b.record()
+        torch.cuda.synchronize()
+        if i:
+            e_ms += a.elapsed_time(b); e_moves += c["moves"]
+    (mx, sm) = reduce_max_sum([ms, float(moves), float(evals), e_ms, float(e_moves)], ctx, world)
+    ms, e_ms = mx[0], mx[3]
+    moves, evals, e_moves = sm[1], sm[2], sm[4]
+    if rank == 0:
+        F = F_OF_N[n]
+        peak, how = peaks()
+        E = evals / max(moves, 1)
+        bpm = 16 + 4 * F * E
+        value = moves / (ms * 1e-3)
+        ach = value / world * bpm / 1e9
+        sector = value / world * (16 + 32 * F * E) / 1e9
+        line = {"metric": "greedy_moves_per_sec", "value": value, "unit": "moves/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"BASELINE configs[3] shape: Q_agent n={n} greedy play of {B} seeded games per GPU to "
+                                       f"completion, seeded random-init weights" + (f" + {args.pretrain} TD lock-steps" if args.pretrain else ""),
+                           "n": n, "games_per_gpu": B, "moves_per_game": moves / world / args.steps / B,
+                           "l2": "a 256 MiB buffer is written between timed steps to flush L2"},
+                "clocks": clocks,
+                "e2e": {"value": e_moves / (e_ms * 1e-3), "unit": "moves/s", "h2d_bytes_per_step": wd.numel() * 4,
+                        "d2h_bytes_per_step": B * 8 + cabi.CTR_COUNT * 8},
+                "gpu_launches": None,
+                "roofline": {"bound": "hbm", "kernel": "greedy_play_kernel (4 LUT moves, F-table gather per valid afterstate, "
+                                                       "argmax, Philox spawn; whole games per launch)",
+                             "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                             "peak_source": how, "bytes_per_move": bpm, "evals_per_move": E,
+                             "sector_granular_GBps": sector,
+                             "note": "algorithmic bytes = 16 + 4 F E per move; a random 4-byte gather moves a 32-byte sector, "
+                                     "sector_granular_GBps counts those"},
+                "cpu_baseline": None}
+        if world == 1:
+            from oracle import oracle as orc
+            orc.build()
+            t0 = time.perf_counter()
+            r = orc.play_philox(n, w_host.numpy(), seed=0, first_id=0, num=min(B, args.cpu_games), threads=orc.max_threads())
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": r["total_moves"] / dt, "unit": "moves/s", "cores": orc.max_threads(), "kind": "port",
+                                    "sample": f"{min(B, args.cpu_games)} of the same games ({dt:.1f} s)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_sweep(args):
+    """BASELINE configs[4]: `--boards` packed boards per GPU x 4 directions: afterstates, merge scores, changed /
+    overflow flags and a Philox spawn on every changed afterstate (b2048_sweep), inputs larger than L2."""
+    import torch
+    import torch.distributed as dist
+    rank, world, local = dist_setup()
+    importlib.import_module("2048_b200")
+    from game2048 import engine
+    ctx = engine.Context.get()
+    m = args.boards
+    gen = torch.Generator(device=ctx.device).manual_seed(rank)       # cell iid: empty p=0.3 else exponent 1..11
+    boards = None
+    chunk = 1 << 22
+    parts = []
+    for i in range(0, m, chunk):
+        k = min(chunk, m - i)
+        cells = torch.randint(1, 12, (k, 16), dtype=torch.int32, device=ctx.device, generator=gen)
+        cells.mul_((torch.rand((k, 16), device=ctx.device, generator=gen) >= 0.3).to(torch.int32))
+        parts.append(ctx.pack(cells))
+    boards = torch.cat(parts)
+    del parts
+    bufs = ctx.sweep(boards, seed=0)
+    host_in = torch.empty(m, dtype=torch.int64).pin_memory()
+    host_in.copy_(boards)
+    host_out = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in bufs]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start(); sampler.wait_first()
+    for _ in range(args.warmup):
+        ctx.sweep(boards, seed=0, out=bufs)
+    barrier()
+    sampler.mark()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for a, b in ev:                                              # 128 MiB in + 1.3 GB out per step: larger than L2
+        a.record()
+        ctx.sweep(boards, seed=0, first_index=rank * m, out=bufs)
+        b.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    e_ms = 0.0
+    for i in range(3):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        boards.copy_(host_in, non_blocking=True)
+        ctx.sweep(boards, seed=0, first_index=rank * m, out=bufs)
+        for h, t in zip(host_out, bufs):
+            h.copy_(t, non_blocking=True)
+        b.record()
+        torch.cuda.synchronize()
+        if i:
+            e_ms += a.elapsed_time(b) / 2
+    (mx, _) = reduce_max_sum([ms, e_ms], ctx, world)
+    if rank == 0:
+        peak, how = peaks()
+        value = world * m * args.steps / (mx[0] * 1e-3)
+        ach = value / world * 89 / 1e9
+        line = {"metric": "sweep_boards_per_sec", "value": value, "unit": "boards/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": mx[0] / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+                "config": {"workload": f"BASELINE configs[4]: {m} packed boards per GPU x 4 directions move/merge/score + spawn",
+                           "boards_per_gpu": m, "l2": "inputs + outputs (1.4 GB per step) are larger than L2"},
+                "clocks": clocks,
+                "e2e": {"value": world * m / (mx[1] * 1e-3), "unit": "boards/s", "h2d_bytes_per_step": m * 8,
+                        "d2h_bytes_per_step": m * 81},
+                "gpu_launches": args.steps,
+                "roofline": {"bound": "hbm", "kernel": "sweep_kernel (row LUT in shared memory, persistent grid)", "achieved": ach,
+                             "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": how,
+                             "bytes_per_board": 89},
+                "cpu_baseline": None}
+        if world == 1:
+            from oracle import oracle as orc
+            orc.build()
+            k = min(m, 1 << 22)
+            hb = host_in.numpy().view(np.uint64)[:k]
+            t0 = time.perf_counter()
+            orc.sweep(hb, seed=0, threads=orc.max_threads())
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": k / dt, "unit": "boards/s", "cores": orc.max_threads(), "kind": "port",
+                                    "sample": f"the first {k} boards ({dt:.1f} s)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
+    if args.workload == "greedy" and args.n == 4 and "--n" not in sys.argv:
+        args.n = 6
+    if args.workload == "greedy" and "--games" not in sys.argv:
+        args.games = 131072
     if args.impl == "reference":
+        if args.workload != "td":
+            raise SystemExit("--impl reference is the td workload (the headline); greedy / sweep lines carry cpu_baseline")
         run_reference(args)
         return
-    if args.workload != "td":
-        raise SystemExit("only --workload td is wired as a bench line in this round; greedy and sweep are reported in extras")
-    run_td(args)
+    {"td": run_td, "greedy": run_greedy, "sweep": run_sweep}[args.workload](args)
 
 
 if __name__ == "__main__":
