@@ -135,6 +135,15 @@ def mode_bits(cabi, args):
            (cabi.UPD_MEAN if args.rule == "mean" else cabi.UPD_SUM) | (cabi.RUN_STEPWISE if args.stepwise else 0)
 
 
+def ncu_traffic(key, field):
+    """bytes per unit of work measured by ncu (profiles/ncu_traffic.json), or None"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return float(json.load(f)[key][field])
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def launches_per_step_of(st, S):
     """kernel launches one bench step (S lock-steps) costs on this rank, sync kernels excluded"""
     from game2048 import cabi
@@ -307,8 +316,12 @@ def run_td(args):
         roof = {"bound": "hbm", "kernel": "td_persist_kernel (phase A gather + argmax + spawn, phase B 8F-way scatter, "
                                           "apply; one cooperative launch per bench step)" if persistent else
                                           "td_phase_a + td_accum + td_apply (stepwise path)",
-                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": how,
-                "launch_us": launch_s * 1e6, "updates_per_launch": per_gpu_updates_per_launch,
+                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": (lambda t: t * per_gpu_updates_per_launch if t and n == 4 and B == 4096 else None)(
+                    ncu_traffic("td_persist_n4_B4096_atomic_mean", "bytes_per_update")),
+                "traffic_source": "profiles/ncu_traffic.json: DRAM bytes per update of one ncu --set full capture of this kernel "
+                                  "(n=4, 4096 games) x updates per launch; the tables never leave L2",
+                "peak_source": how, "launch_us": launch_s * 1e6, "updates_per_launch": per_gpu_updates_per_launch,
                 "bytes_per_update": bytes_per_update(n, e_per_move), "evals_per_move": e_per_move,
                 "atomics_per_sec": value / world * 8 * F,
                 "atomic_issue_peak_per_sec": 126e9,
@@ -507,7 +520,9 @@ def run_greedy(args):
                 "gpu_launches": None,
                 "roofline": {"bound": "hbm", "kernel": "greedy_play_kernel (4 LUT moves, F-table gather per valid afterstate, "
                                                        "argmax, Philox spawn; whole games per launch)",
-                             "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                             "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                             "traffic": (lambda t: t * moves / world / args.steps if t and n == 6 and not args.pretrain else None)(
+                                 ncu_traffic("greedy_n6_B131072_random_init", "bytes_per_move")),
                              "peak_source": how, "bytes_per_move": bpm, "evals_per_move": E,
                              "sector_granular_GBps": sector,
                              "note": "algorithmic bytes = 16 + 4 F E per move; a random 4-byte gather moves a 32-byte sector, "
@@ -601,8 +616,9 @@ def run_sweep(args):
                         "d2h_bytes_per_step": m * 81},
                 "gpu_launches": args.steps,
                 "roofline": {"bound": "hbm", "kernel": "sweep_kernel (row LUT in shared memory, persistent grid)", "achieved": ach,
-                             "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": how,
-                             "bytes_per_board": 89},
+                             "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                             "traffic": (lambda t: t * m if t else None)(ncu_traffic("sweep_16M", "bytes_per_board")),
+                             "peak_source": how, "bytes_per_board": 89},
                 "cpu_baseline": None}
         if world == 1:
             from oracle import oracle as orc
