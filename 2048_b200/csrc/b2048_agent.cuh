@@ -920,7 +920,12 @@ td_persist_kernel(PersistBuffers pb, PersistCtrl *ctrl, const uint32_t *__restri
         if (tl) tl[1] = clock64();
         // ---- phase B: one thread per (entry, table); image s: key, duplicate test against the lower images,
         //      atomic -- issued image by image so that the key arithmetic overlaps the atomics in flight
-        uint32_t idx[8], first = 0, dirty = 0;                // FAST: survive the barrier (the thread applies them)
+        // FAST: these survive the barrier (the thread applies / flushes its own keys).  The values returned by the
+        // global atomics are NOT consumed before the grid barrier: the wait for them overlaps the flush and the
+        // barrier itself (the barrier's release fence orders every atomic of the CTA before the arrival anyway).
+        uint32_t idx[8], first = 0, dirty = 0;
+        float oldf[8];
+        uint32_t oldu[8], oldc[8];
         for (int r = 0; r < rounds; r++) {
             const int e = r * EPR + erow;
             const bool on = worker && e < nslots;
@@ -946,9 +951,6 @@ td_persist_kernel(PersistBuffers pb, PersistCtrl *ctrl, const uint32_t *__restri
             }
             const bool live = on && (EXACT ? isfinite(d) : !isnan(d));
             const long long qd = (EXACT && live) ? quantize(d) : 0;
-            float oldf[8];
-            uint32_t oldu[8];
-            dirty = 0;
 #pragma unroll
             for (int s = 0; s < 8; s++) {
                 uint32_t v = 0;
@@ -964,6 +966,7 @@ td_persist_kernel(PersistBuffers pb, PersistCtrl *ctrl, const uint32_t *__restri
                 for (int o = 0; o < s; o++) ld &= idx[o] != v;
                 oldf[s] = 1.0f;
                 oldu[s] = 1u;
+                oldc[s] = 1u;
                 if (!live) continue;
                 if ((v & big_mask) == 0 && !base14) {         // small-exponent key: shared memory
                     uint32_t cmp = 0;
@@ -971,7 +974,7 @@ td_persist_kernel(PersistBuffers pb, PersistCtrl *ctrl, const uint32_t *__restri
                     for (int k = 0; k < MAXC; k++) cmp |= ((v >> (4 * k)) & 3u) << (2 * k);
                     const int di = dense_off + int(cmp);
                     if (EXACT) atomicAdd(s_q + di, (unsigned long long)qd); else atomicAdd(s_sum + di, d);
-                    if (ld && atomicAdd(s_cnt + di, 1u) == 0u) dirty |= 1u << s;
+                    if (ld) oldc[s] = atomicAdd(s_cnt + di, 1u);
                 } else {
                     const uint32_t k = key_off + v;
                     if (DIRECT) {
@@ -987,12 +990,15 @@ td_persist_kernel(PersistBuffers pb, PersistCtrl *ctrl, const uint32_t *__restri
                     }
                 }
             }
-            first = 0;
-            if (!DIRECT) {
+            dirty = 0;
 #pragma unroll
-                for (int s = 0; s < 8; s++) first |= uint32_t(EXACT ? (oldu[s] == 0u) : (oldf[s] == 0.0f)) << s;
-            }
+            for (int s = 0; s < 8; s++) dirty |= uint32_t(oldc[s] == 0u) << s;
             if (!FAST) {
+                first = 0;
+                if (!DIRECT) {
+#pragma unroll
+                    for (int s = 0; s < 8; s++) first |= uint32_t(EXACT ? (oldu[s] == 0u) : (oldf[s] == 0.0f)) << s;
+                }
                 // first touches -> the CTA's key list; first small-key touches -> its dirty list (one warp scan)
                 const uint32_t mine = __popc(first) | (__popc(dirty) << 16);
                 uint32_t incl = mine;
@@ -1079,6 +1085,9 @@ td_persist_kernel(PersistBuffers pb, PersistCtrl *ctrl, const uint32_t *__restri
                 add_weight(pb.w, pb.delta, k, u);
             };
             if (FAST) {
+                first = 0;
+#pragma unroll
+                for (int s = 0; s < 8; s++) first |= uint32_t(EXACT ? (oldu[s] == 0u) : (oldf[s] == 0.0f)) << s;
                 // the keys this thread touched first (registers): every load first, then the arithmetic and the
                 // stores -- one L2 round trip for up to 8 keys instead of one per key
                 float2 av[8];

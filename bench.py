@@ -277,27 +277,32 @@ def run_td(args):
         ms, upd, mv, evals = float(tmax[0]), float(tsum[1]), float(tsum[2]), float(tsum[3])
     value = upd / (ms * 1e-3)
 
-    # ---- e2e: the same step through host buffers: weights H2D (pinned) -> S lock-steps -> weights + counters D2H
+    # ---- e2e: the same step through host buffers: weights H2D (pinned) -> S lock-steps (with the NCCL delta syncs
+    # at N > 1) -> weights + counters D2H, all inside the timed region; max over ranks, updates summed
     e2e_ms, e2e_upd = 0.0, 0
-    h2d = d2h = 0
-    if world == 1:
-        for i in range(args.steps + 1):
-            cA = games.read_counters()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            torch.cuda.synchronize()
-            a.record()
-            wd.copy_(w_host, non_blocking=True)
-            tr.run(S)
-            w_host.copy_(wd, non_blocking=True)
-            cnt = games.counters.cpu()                           # D2H read of the step's result
-            b.record()
-            torch.cuda.synchronize()
-            if i:                                                # first pass = warm-up
-                e2e_ms += a.elapsed_time(b)
-                e2e_upd += int(cnt[cabi.CTR_UPDATES]) - cA["updates"]
-        h2d, d2h = wd.numel() * 4, wd.numel() * 4 + cabi.CTR_COUNT * 8
-    else:
-        e2e_ms, e2e_upd = ms, upd                                # multi-GPU: weights stay resident between syncs
+    for i in range(min(args.steps, 5) + 1):
+        cA = games.read_counters()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        a.record()
+        wd.copy_(w_host, non_blocking=True)
+        if st.w_sync is not None:
+            st.w_sync.copy_(wd)                                  # replicas restart from the same host weights
+        st.run(S)
+        w_host.copy_(wd, non_blocking=True)
+        cnt = games.counters.cpu()                               # D2H read of the step's result
+        b.record()
+        torch.cuda.synchronize()
+        if i:                                                    # first pass = warm-up
+            e2e_ms += a.elapsed_time(b)
+            e2e_upd += int(cnt[cabi.CTR_UPDATES]) - cA["updates"]
+    h2d, d2h = wd.numel() * 4, wd.numel() * 4 + cabi.CTR_COUNT * 8
+    if world > 1:
+        t2 = torch.tensor([e2e_ms, float(e2e_upd)], dtype=torch.float64, device=ctx.device)
+        tm, ts = t2.clone(), t2.clone()
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+        e2e_ms, e2e_upd = float(tm[0]), float(ts[1])
     e2e = {"value": e2e_upd / (e2e_ms * 1e-3) if e2e_ms else None, "unit": "updates/s",
            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
 
@@ -309,8 +314,11 @@ def run_td(args):
         F = F_OF_N[n]
         peak, how = peaks()
         e_per_move = evals / max(mv, 1)
-        per_gpu_updates_per_launch = upd / world / args.steps
-        launch_s = ms * 1e-3 / args.steps
+        # N > 1: a step is S / sync_every persistent launches with a delta sync after each; the average below then
+        # includes the sync kernels and the allreduce (whole-step view)
+        n_persist = 1 if world == 1 else max(1, -(-S // args.sync_every))
+        per_gpu_updates_per_launch = upd / world / args.steps / n_persist
+        launch_s = ms * 1e-3 / args.steps / n_persist
         ach = per_gpu_updates_per_launch * bytes_per_update(n, e_per_move) / launch_s / 1e9
         persistent = launches_per_step_of(st, S) == 1
         roof = {"bound": "hbm", "kernel": "td_persist_kernel (phase A gather + argmax + spawn, phase B 8F-way scatter, "
