@@ -266,6 +266,17 @@ __global__ void delta_pack_kernel(const float *__restrict__ delta, float *__rest
     }
 }
 
+__global__ void delta_pack_diff_kernel(const float *__restrict__ w, const float *__restrict__ w_sync,
+                                       float *__restrict__ packed, int64_t count)
+{
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < count; i += stride) {
+        const float a = w[i], b = w_sync[i];
+        packed[i] = __fsub_rn(a, b);
+        packed[count + i] = a != b ? 1.0f : 0.0f;
+    }
+}
+
 __global__ void delta_apply_kernel(float *__restrict__ w, float *__restrict__ w_sync, float *__restrict__ delta,
                                    const float *__restrict__ delta_sum, const float *__restrict__ contributors,
                                    int64_t count)
@@ -280,7 +291,7 @@ __global__ void delta_apply_kernel(float *__restrict__ w, float *__restrict__ w_
         float v = __fadd_rn(w_sync[i], s);
         w_sync[i] = v;
         w[i] = v;
-        delta[i] = 0.0f;
+        if (delta) delta[i] = 0.0f;
     }
 }
 
@@ -520,10 +531,19 @@ int b2048_delta_pack(const float *delta, float *packed, int64_t count, b2048_str
     return launch_status();
 }
 
+int b2048_delta_pack_diff(const float *weights, const float *w_sync, float *packed, int64_t count, b2048_stream_t stream)
+{
+    if (count < 0 || (count && (!weights || !w_sync || !packed))) return B2048_EINVAL;
+    if (!count) return 0;
+    int64_t want = cdiv(count, 256), cap = int64_t(sm_count()) * 8;
+    delta_pack_diff_kernel<<<unsigned(want < cap ? want : cap), 256, 0, S(stream)>>>(weights, w_sync, packed, count);
+    return launch_status();
+}
+
 int b2048_delta_apply(float *weights, float *w_sync, float *delta, const float *delta_sum, const float *contributors,
                       int64_t count, b2048_stream_t stream)
 {
-    if (count < 0 || (count && (!weights || !w_sync || !delta || !delta_sum))) return B2048_EINVAL;
+    if (count < 0 || (count && (!weights || !w_sync || !delta_sum))) return B2048_EINVAL;
     if (!count) return 0;
     int64_t want = cdiv(count, 256), cap = int64_t(sm_count()) * 8;
     delta_apply_kernel<<<unsigned(want < cap ? want : cap), 256, 0, S(stream)>>>(weights, w_sync, delta, delta_sum,

@@ -1,6 +1,6 @@
 """Data parallelism over games (the only parallelism the path has): one process per GPU, game slots
 sharded by contiguous global slot ranges, weight tables replicated, and -- for training only -- one exchange:
-every `sync_every` lock-steps the per-rank weight deltas are allreduced (NCCL over NVLink/NVSwitch through
+every `sync_every` lock-steps the per-rank weight deltas (w - w_sync) are allreduced (NCCL over NVLink/NVSwitch through
 torch.distributed) and applied with the per-key mean over contributing ranks (b2048_delta_pack / _apply).
 Greedy play needs no collective at all (Philox streams are keyed by GLOBAL game id, so N ranks reproduce the
 1-rank games exactly); only the final per-game statistics are gathered.
@@ -52,15 +52,15 @@ class CudaOps:
     def counters(self, trainer):
         return trainer.games.read_counters()
 
-    def delta_pack(self, delta, packed):
-        cabi.check(self.ctx.lib.b2048_delta_pack(engine.dptr(delta), engine.dptr(packed), delta.numel(),
-                                                 engine.cur_stream()), "delta_pack")
+    def delta_pack(self, w, w_sync, packed):
+        """packed = [w - w_sync | (w != w_sync)]: what this rank's weights moved by since the last sync"""
+        cabi.check(self.ctx.lib.b2048_delta_pack_diff(engine.dptr(w), engine.dptr(w_sync), engine.dptr(packed), w.numel(),
+                                                      engine.cur_stream()), "delta_pack_diff")
 
-    def delta_apply(self, w, w_sync, delta, packed):
+    def delta_apply(self, w, w_sync, packed):
         n = w.numel()
-        cabi.check(self.ctx.lib.b2048_delta_apply(engine.dptr(w), engine.dptr(w_sync), engine.dptr(delta),
-                                                  engine.dptr(packed), engine.dptr(packed[n:]), n, engine.cur_stream()),
-                   "delta_apply")
+        cabi.check(self.ctx.lib.b2048_delta_apply(engine.dptr(w), engine.dptr(w_sync), None, engine.dptr(packed),
+                                                  engine.dptr(packed[n:]), n, engine.cur_stream()), "delta_apply")
 
     def greedy(self, n, w, seed, first_id, count, limit_tile=0):
         games = engine.GameBatch(count, seed=seed, ctx=self.ctx).init(first_id=first_id)
@@ -88,7 +88,7 @@ class ShardedTrainer:
         self.B = int(games_per_rank)
         self.w = self.ops.weights(weights_flat)
         multi = self.world > 1
-        self.delta = self.ops.zeros_like_weights(self.w) if multi else None
+        self.delta = None            # the kernels keep no second accumulator: delta = w - w_sync at sync time
         self.w_sync = self.w.clone() if multi else None
         self.packed = self.ops.zeros_like_weights(self.w, 2) if multi else None
         # global slot s = rank * B + local slot; a finished game's successor is id + world * B
@@ -106,9 +106,9 @@ class ShardedTrainer:
         """allreduce(sum) of [delta | touched indicator], then w_sync += sum / contributors on every rank"""
         if self.world == 1 or self.since_sync == 0:
             return
-        self.ops.delta_pack(self.delta, self.packed)
+        self.ops.delta_pack(self.w, self.w_sync, self.packed)
         dist.all_reduce(self.packed, op=dist.ReduceOp.SUM, group=self.group)
-        self.ops.delta_apply(self.w, self.w_sync, self.delta, self.packed)
+        self.ops.delta_apply(self.w, self.w_sync, self.packed)
         self.since_sync = 0
         self.syncs += 1
 

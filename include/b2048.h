@@ -235,6 +235,11 @@ int b2048_td_run(int n, float *weights, float *delta, const uint32_t *lut, const
  * every rank touched gets their mean) -- one fused pass, replicas end bit-identical.  contributors == NULL
  * gives the plain sum  w_sync += delta_sum. */
 int b2048_delta_pack(const float *delta, float *packed, int64_t count, b2048_stream_t stream);
+/* The same packing without a delta buffer in the training kernels: delta := weights - w_sync (what this rank's
+ * weights moved by since the last sync), packed[count..2count) = (weights != w_sync).  With it the hot loop needs
+ * no second accumulation (delta = NULL in b2048_td_run) and b2048_delta_apply takes delta = NULL. */
+int b2048_delta_pack_diff(const float *weights, const float *w_sync, float *packed, int64_t count,
+                          b2048_stream_t stream);
 int b2048_delta_apply(float *weights, float *w_sync, float *delta, const float *delta_sum, const float *contributors,
                       int64_t count, b2048_stream_t stream);
 

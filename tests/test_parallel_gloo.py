@@ -34,29 +34,25 @@ class OracleOps:
         rule = 4 if mode & 2 else 3                         # DETERMINISTIC | MEAN / SUM
         ls = self.orc.LockStep(n, w.numpy(), alpha, seed, B, first_id=first_id, id_stride=id_stride, segmented=rule,
                                threads=1)
-        ls.delta, ls.w_t = delta, w
+        assert delta is None                                 # delta = w - w_sync at sync time, no second accumulator
         return ls
 
     def run(self, ls, steps):
-        before = ls.w_t.clone()
         ls.run(steps)
-        if ls.delta is not None:
-            ls.delta += ls.w_t - before                      # the device accumulates the same increments
 
     def counters(self, ls):
         return {"updates": ls.n_updates, "moves": ls.n_moves, "finished": int(ls.fin[0])}
 
-    def delta_pack(self, delta, packed):
-        n = delta.numel()
-        packed[:n] = delta
-        packed[n:] = (delta != 0).float()
+    def delta_pack(self, w, w_sync, packed):
+        n = w.numel()
+        packed[:n] = w - w_sync
+        packed[n:] = (w != w_sync).float()
 
-    def delta_apply(self, w, w_sync, delta, packed):
+    def delta_apply(self, w, w_sync, packed):
         n = w.numel()
         c = packed[n:].clamp(min=1.0)
         w_sync += packed[:n] / c
         w.copy_(w_sync)
-        delta.zero_()
 
     def greedy(self, n, w, seed, first_id, count, limit_tile=0):
         r = self.orc.play_philox(n, w.numpy(), seed, first_id, count, limit_tile=limit_tile, threads=1)
