@@ -36,7 +36,7 @@ def build(force=False, verbose=False):
         return SO
     nvcc = os.environ.get("NVCC", "nvcc")
     os.makedirs(OBJ, exist_ok=True)
-    extra = ["-Xptxas=-v"] if verbose else []
+    extra = (["-Xptxas=-v"] if verbose else []) + os.environ.get("B2048_NVCC_EXTRA", "").split()
     jobs = [([nvcc] + NVCC_FLAGS + extra + ["-c", COMMON, "-o", os.path.join(OBJ, "common.o")])]
     for n in SIZES:
         jobs.append([nvcc] + NVCC_FLAGS + extra + [f"-DB2048_N={n}", "-c", AGENT, "-o", os.path.join(OBJ, f"agent{n}.o")])

@@ -420,8 +420,11 @@ __device__ __forceinline__ void best_move(const float *__restrict__ w, const Lut
     best_dir = bd;
 }
 
+#ifndef B2048_GREEDY_MINBLOCKS
+#define B2048_GREEDY_MINBLOCKS 6
+#endif
 template <int N>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, B2048_GREEDY_MINBLOCKS)
 greedy_play_kernel(const float *__restrict__ w, const uint32_t *__restrict__ lut, b2048_games_t g, int max_steps,
                    int limit_tile, int step_limit, b2048_replay_t rp, int has_replay, int8_t *__restrict__ trace_dir,
                    float *__restrict__ trace_value, uint16_t *__restrict__ trace_spawn, int64_t trace_len)

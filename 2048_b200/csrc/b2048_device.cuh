@@ -398,6 +398,70 @@ __host__ __device__ __forceinline__ void for_each_feature(Fn &&f)
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// All F table indices of one board at once for n = 4, 5, 6 (f_4 / f_5 / f_6, r_learning.py:40-69), sharing work
+// between the tuples instead of extracting every cell of every tuple (feat_index): the same indices with a third
+// of the instructions, which is half of what greedy play executes.
+//   rows / columns   16-bit fields of the board and of its transpose
+//   2x2 squares      (r,c),(r+1,c) is a byte of column c in the transpose: index = pair(c,r) << 8 | pair(c+1,r)
+//   crosses          3 cells of column j and 3 cells of row i around the centre
+//   3x2 / 2x3 rects  base-14 value of 3 consecutive cells of a column / row (16 of them), index = a * 14^3 + b
+// ------------------------------------------------------------------------------------------------
+template <int N>
+__host__ __device__ __forceinline__ void feature_indices_fast(uint64_t b, uint32_t (&idx)[num_feat(N)])
+{
+    static_assert(N >= 4 && N <= 6, "n = 4, 5, 6");
+    const uint64_t bt = transpose(b);
+    const uint32_t row[4] = {uint32_t(b >> 48), uint32_t(b >> 32) & 0xFFFFu, uint32_t(b >> 16) & 0xFFFFu,
+                             uint32_t(b) & 0xFFFFu};
+    const uint32_t col[4] = {uint32_t(bt >> 48), uint32_t(bt >> 32) & 0xFFFFu, uint32_t(bt >> 16) & 0xFFFFu,
+                             uint32_t(bt) & 0xFFFFu};
+#pragma unroll
+    for (int c = 0; c < 4; c++) idx[c] = col[c];                       // x[0,c] x[1,c] x[2,c] x[3,c]
+#pragma unroll
+    for (int r = 0; r < 4; r++) idx[4 + r] = row[r];                   // x[r,0] x[r,1] x[r,2] x[r,3]
+    uint32_t pair[4][3];                                               // x[r,c] << 4 | x[r+1,c]
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+#pragma unroll
+        for (int r = 0; r < 3; r++) pair[c][r] = (col[c] >> (8 - 4 * r)) & 0xFFu;
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) idx[8 + 3 * r + c] = (pair[c][r] << 8) | pair[c + 1][r];
+    if constexpr (N >= 5) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {                                  // centre (i,j), i,j in {1,2}, row-major
+            const int i = 1 + q / 2, j = 1 + q % 2;
+            const uint32_t v3 = (col[j] >> (4 * (2 - i))) & 0xFFFu;    // x[i-1,j] x[i,j] x[i+1,j]
+            const uint32_t h3 = (row[i] >> (4 * (2 - j))) & 0xFFFu;    // x[i,j-1] x[i,j] x[i,j+1]
+            idx[17 + q] = ((v3 & 0x0F0u) << 12) | ((v3 & 0xF00u) << 4) | (h3 & 0xF00u) | ((v3 & 0x00Fu) << 4) | (h3 & 0x00Fu);
+        }
+    }
+    if constexpr (N == 6) {
+        const uint64_t y = clamp13(b), yt = clamp13(bt);               // min(x, 13) commutes with the transpose
+        uint32_t v3[4][2], h3[4][2];                                   // base-14 value of 3 consecutive cells
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t yc = uint32_t(yt >> (48 - 16 * k)) & 0xFFFFu, yr = uint32_t(y >> (48 - 16 * k)) & 0xFFFFu;
+#pragma unroll
+            for (int o = 0; o < 2; o++) {
+                const uint32_t fc = (yc >> (4 - 4 * o)) & 0xFFFu, fr = (yr >> (4 - 4 * o)) & 0xFFFu;
+                v3[k][o] = (fc >> 8) * 196u + ((fc >> 4) & 15u) * 14u + (fc & 15u);
+                h3[k][o] = (fr >> 8) * 196u + ((fr >> 4) & 15u) * 14u + (fr & 15u);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 2; r++)                                    // 3x2: column c rows r..r+2, then column c+1
+#pragma unroll
+            for (int c = 0; c < 3; c++) idx[21 + 3 * r + c] = v3[c][r] * 2744u + v3[c + 1][r];
+#pragma unroll
+        for (int r = 0; r < 3; r++)                                    // 2x3: row r columns c..c+2, then row r+1
+#pragma unroll
+            for (int c = 0; c < 2; c++) idx[27 + 2 * r + c] = h3[r][c] * 2744u + h3[r + 1][c];
+    }
+}
+
 // QAgent.evaluate (r_learning.py:202-203): sequential float32 sum in table order, from 0.
 // COHERENT: read through L2 (ld.global.cg) instead of the non-coherent L1 path -- required inside the
 // persistent training kernel, where other SMs update the tables between lock-steps of the same launch.
@@ -405,13 +469,22 @@ template <int N, bool COHERENT = false>
 __device__ __forceinline__ float evaluate(const float *__restrict__ w, uint64_t b)
 {
     constexpr int F = num_feat(N);
-    const uint64_t y = (N == 6) ? clamp13(b) : 0;
     float v[F];
-    for_each_feature<N>([&](auto I) {
-        constexpr int i = decltype(I)::value;
-        const float *p = w + table_offset(N, i) + feat_index<N, i>(b, y);
-        v[i] = COHERENT ? __ldcg(p) : __ldg(p);                           // all gathers in flight first
-    });
+    if constexpr (N >= 4) {
+        uint32_t idx[F];
+        feature_indices_fast<N>(b, idx);
+        for_each_feature<N>([&](auto I) {
+            constexpr int i = decltype(I)::value;
+            const float *p = w + table_offset(N, i) + idx[i];
+            v[i] = COHERENT ? __ldcg(p) : __ldg(p);                       // all gathers in flight first
+        });
+    } else {
+        for_each_feature<N>([&](auto I) {
+            constexpr int i = decltype(I)::value;
+            const float *p = w + table_offset(N, i) + feat_index<N, i>(b, 0);
+            v[i] = COHERENT ? __ldcg(p) : __ldg(p);
+        });
+    }
     float acc = 0.0f;
 #pragma unroll
     for (int i = 0; i < F; i++) acc = __fadd_rn(acc, v[i]);

@@ -39,6 +39,18 @@ static void features_n(const uint64_t *boards, int64_t m, int32_t *feat)
     }
 }
 
+// the shared-work index routine the evaluate kernels use for n >= 4 (must equal feat_index table by table)
+template <int N>
+static void features_fast_n(const uint64_t *boards, int64_t m, int32_t *feat)
+{
+    constexpr int F = num_feat(N);
+    for (int64_t q = 0; q < m; q++) {
+        uint32_t idx[F];
+        feature_indices_fast<N>(boards[q], idx);
+        for (int i = 0; i < F; i++) feat[q * F + i] = int32_t(idx[i]);
+    }
+}
+
 extern "C" {
 
 void hs_lut(uint32_t *lut)
@@ -86,6 +98,17 @@ int hs_features(int n, const uint64_t *boards, int64_t m, int32_t *feat)
     case 4: features_n<4>(boards, m, feat); break;
     case 5: features_n<5>(boards, m, feat); break;
     case 6: features_n<6>(boards, m, feat); break;
+    default: return -1;
+    }
+    return num_feat(n);
+}
+
+int hs_features_fast(int n, const uint64_t *boards, int64_t m, int32_t *feat)
+{
+    switch (n) {
+    case 4: features_fast_n<4>(boards, m, feat); break;
+    case 5: features_fast_n<5>(boards, m, feat); break;
+    case 6: features_fast_n<6>(boards, m, feat); break;
     default: return -1;
     }
     return num_feat(n);

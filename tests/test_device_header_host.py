@@ -33,6 +33,7 @@ def hs():
     lib.hs_move4.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64] + [C.c_void_p] * 4
     lib.hs_stats.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
     lib.hs_features.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_void_p]
+    lib.hs_features_fast.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_void_p]
     return lib
 
 
@@ -123,6 +124,17 @@ def test_features(hs, orc, n):
     assert hs.hs_features(n, ptr(boards), len(boards), ptr(feat)) == ref.shape[1]
     assert np.array_equal(feat, ref)
     assert [hs.hs_table_offset(n, i) for i in range(ref.shape[1] + 1)] == orc.table_offsets(n).tolist()
+    if n >= 4:                                   # the shared-work routine of the evaluate kernels: same indices
+        fast = np.zeros_like(ref)
+        assert hs.hs_features_fast(n, ptr(boards), len(boards), ptr(fast)) == ref.shape[1]
+        assert np.array_equal(fast, ref)
+        rng = np.random.default_rng(n)
+        rnd = rng.integers(0, 16, size=(20000, 16)).astype(np.int32)              # includes exponents 14, 15 (clamp)
+        rb = orc.pack_np(rnd)
+        a, b = np.zeros((len(rb), ref.shape[1]), np.int32), np.zeros((len(rb), ref.shape[1]), np.int32)
+        hs.hs_features(n, ptr(rb), len(rb), ptr(a))
+        hs.hs_features_fast(n, ptr(rb), len(rb), ptr(b))
+        assert np.array_equal(a, b) and np.array_equal(a, orc.features_batch(n, rnd))
 
 
 def test_d4_images_are_the_reference_set(hs, orc):
