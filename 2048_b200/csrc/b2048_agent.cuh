@@ -393,15 +393,31 @@ __device__ __forceinline__ void log_finished(const b2048_games_t &g, uint64_t id
 
 // One afterstate per lane (lane d of a 4-lane group = direction d), value by n-tuple gather, then a
 // width-4 shuffle argmax with the reference's tie rule (strict '>' scanning d = 0..3: lowest d wins).
-template <int N, bool COHERENT = false>
-__device__ __forceinline__ void best_move(const float *__restrict__ w, const LutGlobal &L, uint64_t board, int d,
-                                          bool run, uint64_t &best_after, uint32_t &best_gain, float &best_value,
-                                          int &best_dir, uint32_t &best_flags, uint32_t &n_valid)
+// Split in two so that the persistent trainer can do the weight-independent half (LUT move, table indices)
+// while it waits at the grid barrier that precedes the next lock-step.
+template <int N>
+struct MovePrep {
+    uint64_t after;
+    uint32_t gain, fl;
+    uint32_t idx[num_feat(N)];
+};
+
+template <int N>
+__device__ __forceinline__ void move_prepare(const LutGlobal &L, uint64_t board, int d, MovePrep<N> &p)
 {
-    uint32_t gain = 0, fl = 0;
-    uint64_t after = move_dir(L, board, d, gain, fl);
-    const bool valid = run && (fl & 1u);
-    float v = valid ? evaluate<N, COHERENT>(w, after) : -INFINITY;
+    p.gain = 0;
+    p.fl = 0;
+    p.after = move_dir(L, board, d, p.gain, p.fl);
+    feature_indices<N>(p.after, p.idx);
+}
+
+template <int N, bool COHERENT = false>
+__device__ __forceinline__ void best_move_finish(const float *__restrict__ w, const MovePrep<N> &p, int d, bool run,
+                                                 uint64_t &best_after, uint32_t &best_gain, float &best_value,
+                                                 int &best_dir, uint32_t &best_flags, uint32_t &n_valid)
+{
+    const bool valid = run && (p.fl & 1u);
+    float v = valid ? gather_sum<N, COHERENT>(w, p.idx) : -INFINITY;
     // a direction that would create 2^16 is kept valid here; the caller stops the game if it wins
     float bv = v;
     int bd = valid ? d : 4;                           // invalid lanes never win ties
@@ -413,11 +429,21 @@ __device__ __forceinline__ void best_move(const float *__restrict__ w, const Lut
     }
     n_valid = __popc(__ballot_sync(FULL, valid) >> ((threadIdx.x & 31) & ~3) & 0xFu);
     const int src = bd & 3;
-    best_after = shfl64(after, src, 4);
-    best_gain = __shfl_sync(FULL, gain, src, 4);
-    best_flags = __shfl_sync(FULL, fl, src, 4);
+    best_after = shfl64(p.after, src, 4);
+    best_gain = __shfl_sync(FULL, p.gain, src, 4);
+    best_flags = __shfl_sync(FULL, p.fl, src, 4);
     best_value = bv;
     best_dir = bd;
+}
+
+template <int N, bool COHERENT = false>
+__device__ __forceinline__ void best_move(const float *__restrict__ w, const LutGlobal &L, uint64_t board, int d,
+                                          bool run, uint64_t &best_after, uint32_t &best_gain, float &best_value,
+                                          int &best_dir, uint32_t &best_flags, uint32_t &n_valid)
+{
+    MovePrep<N> p;
+    move_prepare<N>(L, board, d, p);
+    best_move_finish<N, COHERENT>(w, p, d, run, best_after, best_gain, best_value, best_dir, best_flags, n_valid);
 }
 
 #ifndef B2048_GREEDY_MINBLOCKS
@@ -570,7 +596,7 @@ __device__ __forceinline__ bool phase_a_compute(const float *__restrict__ w, con
                                                 float &dw, const b2048_replay_t &rp, int has_replay,
                                                 int8_t *__restrict__ trace_dir, float *__restrict__ trace_value,
                                                 float *__restrict__ trace_dw, uint16_t *__restrict__ trace_spawn,
-                                                int64_t trace_len, StepCounters &c)
+                                                int64_t trace_len, StepCounters &c, const MovePrep<N> *prep = nullptr)
 {
     constexpr int F = num_feat(N);
     uint64_t board = s.board;
@@ -589,7 +615,8 @@ __device__ __forceinline__ bool phase_a_compute(const float *__restrict__ w, con
     uint32_t bg, bf, nv;
     float bv;
     int bd;
-    best_move<N, COHERENT>(w, L, board, d, run && !over, ba, bg, bv, bd, bf, nv);
+    if (prep) best_move_finish<N, COHERENT>(w, *prep, d, run && !over, ba, bg, bv, bd, bf, nv);   // moves of s.board
+    else best_move<N, COHERENT>(w, L, board, d, run && !over, ba, bg, bv, bd, bf, nv);
     dw = NAN;
     ub = 0;
     if (run) {
@@ -744,18 +771,30 @@ __device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t *p)
 // Arrival = red.release.gpu (MEMBAR.ALL.GPU + RED: the CTA's earlier writes and atomics are performed first);
 // the wait polls with relaxed loads and does NOT invalidate L1 (no CCTL.IVALL): everything another CTA may have
 // written is read with ld.cg (L2) afterwards, while the row LUT and the CTA's own game slots stay L1-resident.
-__device__ __forceinline__ void grid_barrier(uint32_t *bar, uint32_t &target)
+__device__ __forceinline__ void grid_arrive(uint32_t *bar, uint32_t &target)
 {
     __syncthreads();
     if (threadIdx.x == 0) {
         target += gridDim.x;
         asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+    }
+}
+
+__device__ __forceinline__ void grid_wait(const uint32_t *bar, uint32_t target)
+{
+    if (threadIdx.x == 0) {
         // a wait of 2^25 polls (seconds) can only be a lost CTA: trap instead of hanging the device
         uint32_t polls = 0;
         while (ld_relaxed_gpu(bar) < target)
             if (++polls > (1u << 25)) __trap();
     }
     __syncthreads();
+}
+
+__device__ __forceinline__ void grid_barrier(uint32_t *bar, uint32_t &target)
+{
+    grid_arrive(bar, target);
+    grid_wait(bar, target);
 }
 
 // ---- dense small-exponent key space --------------------------------------------------------------
@@ -889,6 +928,11 @@ td_persist_kernel(PersistBuffers pb, PersistCtrl *ctrl, const uint32_t *__restri
     const int dense_off = small_offset_rt<N>(tab);
     const uint32_t big_mask = base14 ? 0u : (0xCCCCCCu & ((1u << (4 * ncell)) - 1u));   // any cell > 3
     const int rounds = (nslots + EPR - 1) / EPR;
+    // FAST: the weight-independent half of phase A (LUT moves of the 4 directions, table indices of the afterstates)
+    // is done one step ahead, between the arrival at and the wait for the grid barrier that precedes phase A
+    constexpr bool PREP = FAST && N <= 5 && !EXACT;        // n = 6 / exact modes: the extra registers would spill
+    MovePrep<N> prep;
+    if (PREP && a_warp) move_prepare<N>(L, st.board, a_dir, prep);
     __syncthreads();
 
     for (int step = 0; step < steps; step++) {
@@ -902,7 +946,7 @@ td_persist_kernel(PersistBuffers pb, PersistCtrl *ctrl, const uint32_t *__restri
                 uint64_t ub;
                 float dw;
                 st_dirty |= phase_a_compute<N, true>(pb.w, L, g, alpha, slot0 + a_slot, a_dir, a_in, st, ub, dw, no_replay, 0,
-                                                     nullptr, nullptr, nullptr, nullptr, 0, c);
+                                                     nullptr, nullptr, nullptr, nullptr, 0, c, PREP ? &prep : nullptr);
                 if (a_in) {                                   // lane d stages images d and 4 + d (d4_image order)
                     uint64_t im = (a_dir & 1) ? flip_h(ub) : ub;
                     if (a_dir & 2) im = flip_v(im);
@@ -1069,7 +1113,9 @@ td_persist_kernel(PersistBuffers pb, PersistCtrl *ctrl, const uint32_t *__restri
             }
         }
         if (tl) tl[3] = clock64();
-        grid_barrier(&ctrl->bar, bar_target);                 // every contribution of the step has landed
+        grid_arrive(&ctrl->bar, bar_target);                  // every contribution of the step has landed
+        if (DIRECT && PREP && a_warp) move_prepare<N>(L, st.board, a_dir, prep);   // W_{t+1} is complete after this one
+        grid_wait(&ctrl->bar, bar_target);
         if (tl) tl[4] = clock64();
         if (!DIRECT) {
             auto apply_key = [&](uint32_t k) {
@@ -1087,6 +1133,21 @@ td_persist_kernel(PersistBuffers pb, PersistCtrl *ctrl, const uint32_t *__restri
                 }
                 add_weight(pb.w, pb.delta, k, u);
             };
+            // this thread's entry of the dense hot table: its loads go out with the first-touch loads below (one L2
+            // round trip for the whole apply phase); the weight index of a dense entry is static
+            const int hq = blockIdx.x * blockDim.x + threadIdx.x;
+            const bool hot_on = FAST && hq < NS;
+            const uint32_t hk = hot_on ? small_to_key<N>(hq) : 0u;
+            float2 hv = make_float2(0.0f, 0.0f);
+            unsigned long long hqv = 0;
+            uint32_t hcv = 0;
+            float hw = 0.0f, hd = 0.0f;
+            if (hot_on) {
+                if (EXACT) { hqv = __ldcg(hotq + hq); hcv = __ldcg(hotc + hq); }
+                else hv = __ldcg(hot2 + hq);
+                hw = __ldcg(pb.w + hk);
+                if (pb.delta) hd = __ldcg(pb.delta + hk);
+            }
             if (FAST) {
                 first = 0;
 #pragma unroll
@@ -1128,7 +1189,16 @@ td_persist_kernel(PersistBuffers pb, PersistCtrl *ctrl, const uint32_t *__restri
                 const uint32_t mine = s_cursor;
                 for (uint32_t q = threadIdx.x; q < mine; q += blockDim.x) apply_key(__ldcg(list + q));
             }
-            for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < NS; q += gridDim.x * blockDim.x) {
+            if (hot_on && (EXACT ? hcv != 0u : hv.y != 0.0f)) {
+                const float u = EXACT ? update_value<true, MEAN>((long long)hqv, 0.0f, float(hcv))
+                                      : update_value<false, MEAN>(0, hv.x, hv.y);
+                if (EXACT) { __stcg(hotq + hq, 0ULL); __stcg(hotc + hq, 0u); }
+                else __stcg(hot2 + hq, make_float2(0.0f, 0.0f));
+                __stcg(pb.w + hk, __fadd_rn(hw, u));
+                if (pb.delta) __stcg(pb.delta + hk, __fadd_rn(hd, u));
+            }
+            for (int q = blockIdx.x * blockDim.x + threadIdx.x + (FAST ? gridDim.x * blockDim.x : 0); q < NS;
+                 q += gridDim.x * blockDim.x) {
                 float u;
                 if (EXACT) {
                     const uint32_t cv = __ldcg(hotc + q);
@@ -1144,9 +1214,10 @@ td_persist_kernel(PersistBuffers pb, PersistCtrl *ctrl, const uint32_t *__restri
                 }
                 add_weight(pb.w, pb.delta, small_to_key<N>(q), u);
             }
-            __syncthreads();
             if (tl) tl[5] = clock64();
-            grid_barrier(&ctrl->bar, bar_target);             // W_{t+1} complete
+            grid_arrive(&ctrl->bar, bar_target);              // W_{t+1} complete once everybody has arrived
+            if (PREP && a_warp) move_prepare<N>(L, st.board, a_dir, prep);
+            grid_wait(&ctrl->bar, bar_target);
         }
         if (tl) tl[6] = clock64();
     }

@@ -462,33 +462,47 @@ __host__ __device__ __forceinline__ void feature_indices_fast(uint64_t b, uint32
     }
 }
 
+// all F table indices of a board (any n), table order
+template <int N>
+__host__ __device__ __forceinline__ void feature_indices(uint64_t b, uint32_t (&idx)[num_feat(N)])
+{
+    if constexpr (N >= 4) {
+        feature_indices_fast<N>(b, idx);
+    } else {
+        for_each_feature<N>([&](auto I) {
+            constexpr int i = decltype(I)::value;
+            idx[i] = feat_index<N, i>(b, 0);
+        });
+    }
+}
+
+// sum of the F weights at precomputed indices: every gather in flight first, then the sequential float32 sum in
+// table order, from 0 (QAgent.evaluate, r_learning.py:202-203)
+template <int N, bool COHERENT = false>
+__device__ __forceinline__ float gather_sum(const float *__restrict__ w, const uint32_t (&idx)[num_feat(N)])
+{
+    constexpr int F = num_feat(N);
+    float v[F];
+    for_each_feature<N>([&](auto I) {
+        constexpr int i = decltype(I)::value;
+        const float *p = w + table_offset(N, i) + idx[i];
+        v[i] = COHERENT ? __ldcg(p) : __ldg(p);
+    });
+    float acc = 0.0f;
+#pragma unroll
+    for (int i = 0; i < F; i++) acc = __fadd_rn(acc, v[i]);
+    return acc;
+}
+
 // QAgent.evaluate (r_learning.py:202-203): sequential float32 sum in table order, from 0.
 // COHERENT: read through L2 (ld.global.cg) instead of the non-coherent L1 path -- required inside the
 // persistent training kernel, where other SMs update the tables between lock-steps of the same launch.
 template <int N, bool COHERENT = false>
 __device__ __forceinline__ float evaluate(const float *__restrict__ w, uint64_t b)
 {
-    constexpr int F = num_feat(N);
-    float v[F];
-    if constexpr (N >= 4) {
-        uint32_t idx[F];
-        feature_indices_fast<N>(b, idx);
-        for_each_feature<N>([&](auto I) {
-            constexpr int i = decltype(I)::value;
-            const float *p = w + table_offset(N, i) + idx[i];
-            v[i] = COHERENT ? __ldcg(p) : __ldg(p);                       // all gathers in flight first
-        });
-    } else {
-        for_each_feature<N>([&](auto I) {
-            constexpr int i = decltype(I)::value;
-            const float *p = w + table_offset(N, i) + feat_index<N, i>(b, 0);
-            v[i] = COHERENT ? __ldcg(p) : __ldg(p);
-        });
-    }
-    float acc = 0.0f;
-#pragma unroll
-    for (int i = 0; i < F; i++) acc = __fadd_rn(acc, v[i]);
-    return acc;
+    uint32_t idx[num_feat(N)];
+    feature_indices<N>(b, idx);
+    return gather_sum<N, COHERENT>(w, idx);
 }
 
 }   // namespace b2048
