@@ -1115,6 +1115,28 @@ td_persist_kernel(PersistBuffers pb, PersistCtrl *ctrl, const uint32_t *__restri
         if (tl) tl[3] = clock64();
         grid_arrive(&ctrl->bar, bar_target);                  // every contribution of the step has landed
         if (DIRECT && PREP && a_warp) move_prepare<N>(L, st.board, a_dir, prep);   // W_{t+1} is complete after this one
+        // FAST apply, the half that does not depend on other CTAs, done while waiting: which keys this thread
+        // touched first (the values returned by its atomics), and the old weights of those keys and of its hot entry
+        // (a key is applied by exactly one thread, so nobody else writes them before this thread does)
+        const int hq = blockIdx.x * blockDim.x + threadIdx.x;
+        const bool hot_on = FAST && !DIRECT && hq < NS;
+        const uint32_t hk = hot_on ? small_to_key<N>(hq) : 0u;
+        float hw = 0.0f, hd = 0.0f, wv[8], dv[8];
+        if (FAST && !DIRECT) {
+            first = 0;
+#pragma unroll
+            for (int s = 0; s < 8; s++) first |= uint32_t(EXACT ? (oldu[s] == 0u) : (oldf[s] == 0.0f)) << s;
+#pragma unroll
+            for (int s = 0; s < 8; s++)
+                if ((first >> s) & 1u) {
+                    wv[s] = __ldcg(pb.w + key_off + idx[s]);
+                    if (pb.delta) dv[s] = __ldcg(pb.delta + key_off + idx[s]);
+                }
+            if (hot_on) {
+                hw = __ldcg(pb.w + hk);
+                if (pb.delta) hd = __ldcg(pb.delta + hk);
+            }
+        }
         grid_wait(&ctrl->bar, bar_target);
         if (tl) tl[4] = clock64();
         if (!DIRECT) {
@@ -1133,39 +1155,27 @@ td_persist_kernel(PersistBuffers pb, PersistCtrl *ctrl, const uint32_t *__restri
                 }
                 add_weight(pb.w, pb.delta, k, u);
             };
-            // this thread's entry of the dense hot table: its loads go out with the first-touch loads below (one L2
-            // round trip for the whole apply phase); the weight index of a dense entry is static
-            const int hq = blockIdx.x * blockDim.x + threadIdx.x;
-            const bool hot_on = FAST && hq < NS;
-            const uint32_t hk = hot_on ? small_to_key<N>(hq) : 0u;
+            // this thread's entry of the dense hot table: its load goes out with the accumulator loads below (one L2
+            // round trip for the whole apply phase)
             float2 hv = make_float2(0.0f, 0.0f);
             unsigned long long hqv = 0;
             uint32_t hcv = 0;
-            float hw = 0.0f, hd = 0.0f;
             if (hot_on) {
                 if (EXACT) { hqv = __ldcg(hotq + hq); hcv = __ldcg(hotc + hq); }
                 else hv = __ldcg(hot2 + hq);
-                hw = __ldcg(pb.w + hk);
-                if (pb.delta) hd = __ldcg(pb.delta + hk);
             }
             if (FAST) {
-                first = 0;
-#pragma unroll
-                for (int s = 0; s < 8; s++) first |= uint32_t(EXACT ? (oldu[s] == 0u) : (oldf[s] == 0.0f)) << s;
-                // the keys this thread touched first (registers): every load first, then the arithmetic and the
-                // stores -- one L2 round trip for up to 8 keys instead of one per key
+                // the keys this thread touched first (registers): every accumulator load first, then the arithmetic
+                // and the stores -- one L2 round trip for up to 8 keys instead of one per key
                 float2 av[8];
                 long long aq[8];
                 uint32_t ac[8];
-                float wv[8], dv[8];
 #pragma unroll
                 for (int s = 0; s < 8; s++) {
                     const uint32_t k = key_off + idx[s];
                     if ((first >> s) & 1u) {
                         if (EXACT) { aq[s] = (long long)__ldcg(accq + k); ac[s] = __ldcg(pb.cnt + k); }
                         else av[s] = __ldcg(acc2 + k);
-                        wv[s] = __ldcg(pb.w + k);
-                        if (pb.delta) dv[s] = __ldcg(pb.delta + k);
                     }
                 }
 #pragma unroll
