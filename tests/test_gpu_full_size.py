@@ -1,0 +1,154 @@
+"""GPU tier, BASELINE.json's full sizes.  Where the CPU oracle finishes in seconds the comparison is exact; beyond
+that the checks are size-independent properties of the domain (tile-sum conservation, direction symmetry of the
+merge score, sharding invariance, run-to-run identity, counter identities)."""
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    sys.path.insert(0, ROOT)
+    importlib.import_module("2048_b200")
+    from game2048 import cabi, engine
+    return engine.Context.get(), engine, cabi
+
+
+def u64(t):
+    return t.detach().cpu().numpy().view(np.uint64)
+
+
+def seeded_weights(n, seed=0):
+    sys.path.insert(0, ROOT)
+    import bench
+    return bench.seeded_weights(n, seed)
+
+
+def tile_sum(boards):
+    """sum of 2^x over the non-empty cells of packed boards (a move conserves it, a spawn adds 2 or 4)"""
+    b = np.asarray(boards, dtype=np.uint64).reshape(-1, 1)
+    x = (b >> (np.uint64(4) * np.arange(16, dtype=np.uint64))) & np.uint64(15)
+    return np.where(x > 0, np.uint64(1) << x, np.uint64(0)).sum(axis=1)
+
+
+def test_config2_td_4096_games_headline_shape(eng, orc):
+    """configs[1]: n=4, 4,096 games on one GPU (147 CTAs x 28 slots, the FAST layout of the persistent kernel):
+    deterministic mode == float32 oracle bit for bit over 150 lock-steps, run-to-run identical; atomic mode within
+    a statistical tolerance of it (a flipped near-tie sends a game down another path)."""
+    ctx, engine, cabi = eng
+    n, B, steps = 4, 4096, 150
+    w0 = seeded_weights(n)
+    ref_w = w0.copy()
+    ls = orc.LockStep(n, ref_w, 0.25, 5, B, segmented=4, threads=orc.max_threads())
+    ls.run(steps)
+    outs = []
+    for rep in range(2):
+        wd = ctx.to_device(w0)
+        games = engine.GameBatch(B, seed=5, ctx=ctx).init()
+        tr = engine.TDTrainer(ctx, n, wd, games, 0.25, cabi.UPD_DETERMINISTIC | cabi.UPD_MEAN)
+        tr.run(steps)
+        outs.append((wd.cpu().numpy(), games.to_host(), games.read_counters()))
+    (wa, ha, ca), (wb, hb, cb) = outs
+    assert np.array_equal(wa, wb) and np.array_equal(ha["board"], hb["board"]) and ca == cb
+    assert np.array_equal(wa, ref_w)
+    assert np.array_equal(ha["board"], ls.board) and np.array_equal(ha["old_label"], ls.old_label)
+    assert ca["updates"] == ls.n_updates and ca["moves"] == ls.n_moves and ca["finished"] == ls.fin[0]
+    # atomic mode: same rule, unordered float adds.  From one common state a single lock-step cannot diverge (all
+    # decisions of the step are taken on identical weights), so the weights must agree element-wise up to the
+    # order of the float sums; over many steps a flipped near-tie would send a game down another path.
+    def clone(src):
+        dst = engine.GameBatch(B, seed=5, ctx=ctx)
+        for name in ("board", "score", "moves", "game_id", "state", "old_label", "flags"):
+            getattr(dst, name).copy_(getattr(src, name))
+        return dst
+
+    wd = ctx.to_device(w0)
+    games = engine.GameBatch(B, seed=5, ctx=ctx).init()
+    engine.TDTrainer(ctx, n, wd, games, 0.25, cabi.UPD_DETERMINISTIC | cabi.UPD_MEAN).run(60)
+    w_det, w_atm = wd.clone(), wd.clone()
+    engine.TDTrainer(ctx, n, w_det, clone(games), 0.25, cabi.UPD_DETERMINISTIC | cabi.UPD_MEAN).run(1)
+    g_atm = clone(games)
+    engine.TDTrainer(ctx, n, w_atm, g_atm, 0.25, cabi.UPD_ATOMIC | cabi.UPD_MEAN).run(1)
+    d_det, d_atm = (w_det - wd).cpu().numpy(), (w_atm - wd).cpu().numpy()
+    assert np.count_nonzero(d_det) > 10000 and np.array_equal(d_det != 0, d_atm != 0)
+    assert np.abs(d_det - d_atm).max() <= 1e-5 * max(np.abs(d_det).max(), 1.0)
+    assert g_atm.read_counters()["updates"] == B
+
+
+def test_config4_greedy_131072_games_n6(eng, orc):
+    """configs[3], one GPU's share: n=6, 131,072 greedy games to completion == the oracle's games (scores, move
+    counts, final boards), and two half-batches (sharding by global game id) reproduce them."""
+    ctx, engine, cabi = eng
+    n, B = 6, 131072
+    w0 = seeded_weights(n)
+    wd = ctx.to_device(w0)
+    games = engine.GameBatch(B, seed=0, ctx=ctx).init()
+    engine.greedy_play(ctx, n, wd, games)
+    h, c = games.to_host(), games.read_counters()
+    ref = orc.play_philox(n, w0, seed=0, first_id=0, num=B, threads=orc.max_threads())
+    assert np.array_equal(h["score"].astype(np.int64), ref["scores"])
+    assert np.array_equal(h["moves"].astype(np.int32), ref["moves"])
+    assert np.array_equal(h["board"], ref["boards"])
+    assert c["moves"] == ref["total_moves"] and c["evals"] == ref["n_eval"] and c["finished"] == B and c["active"] == 0
+    assert c["score_sum"] == int(ref["scores"].sum())
+    half = B // 2
+    b2 = engine.GameBatch(half, seed=0, ctx=ctx).init(first_id=half)
+    engine.greedy_play(ctx, n, wd, b2)
+    assert np.array_equal(b2.to_host()["board"], ref["boards"][half:])
+
+
+def test_config5_sweep_16M_boards(eng, orc):
+    """configs[4]: 16,777,216 boards x 4 directions + spawns.  Exact against the oracle on a 1M-board slice;
+    on all 16M: a move conserves the tile sum unless it overflows, the merge score is the same for opposite
+    directions, changed <=> afterstate != board, every spawn adds exactly one 2 or 4 on an empty cell."""
+    import torch
+    ctx, engine, cabi = eng
+    m = 1 << 24
+    gen = torch.Generator(device=ctx.device).manual_seed(0)
+    parts = []
+    for i in range(0, m, 1 << 22):
+        cells = torch.randint(1, 12, (1 << 22, 16), dtype=torch.int32, device=ctx.device, generator=gen)
+        cells.mul_((torch.rand((1 << 22, 16), device=ctx.device, generator=gen) >= 0.3).to(torch.int32))
+        parts.append(ctx.pack(cells))
+    boards = torch.cat(parts)
+    del parts, cells
+    after, gain, flags, spawned = ctx.sweep(boards, seed=7, first_index=0)
+    hb = u64(boards)
+    k = 1 << 20
+    ra, rg, rf, rs = orc.sweep(hb[:k], seed=7, first_index=0, threads=orc.max_threads())
+    assert np.array_equal(u64(after[:k]), ra) and np.array_equal(gain[:k].cpu().numpy().view(np.uint32), rg)
+    assert np.array_equal(flags[:k].cpu().numpy(), rf) and np.array_equal(u64(spawned[:k]), rs)
+    # properties on all 16M (on the device: torch int64 arithmetic on the packed bits)
+    sh = (4 * torch.arange(16, device=ctx.device, dtype=torch.int64))
+
+    def tsum(t):                                                     # [..., ] int64 packed -> tile sums
+        x = (t.unsqueeze(-1) >> sh) & 15
+        return torch.where(x > 0, torch.ones_like(x) << x, torch.zeros_like(x)).sum(-1)
+
+    g32 = gain.to(torch.int64) & 0xFFFFFFFF
+    assert torch.equal(g32[:, 0], g32[:, 2]) and torch.equal(g32[:, 1], g32[:, 3])
+    fl = flags.to(torch.int64)
+    for lo in range(0, m, 1 << 22):                                   # in chunks: [4M, 4, 16] int64 temporaries
+        s = slice(lo, lo + (1 << 22))
+        base = tsum(boards[s])
+        for d in range(4):
+            ch, ovf = (fl[s] >> d) & 1, (fl[s] >> (4 + d)) & 1
+            a = after[s, d]
+            assert torch.equal(ch.bool() & ~ovf.bool(), (a != boards[s]) & ~ovf.bool())
+            assert torch.equal(tsum(a)[ovf == 0], base[ovf == 0])
+            ok = (ch == 1) & (ovf == 0)
+            added = tsum(spawned[s, d]) - tsum(a)
+            assert bool(((added[ok] == 2) | (added[ok] == 4)).all())
+            assert bool((((spawned[s, d] ^ a)[ok] != 0)).all()) and torch.equal(spawned[s, d][~ok], a[~ok])
+    share4 = float((tsum(spawned[:, 0]) - tsum(after[:, 0]) == 4).float().sum() / ((fl & 1) & ~((fl >> 4) & 1)).sum())
+    assert abs(share4 - 0.1) < 0.002                                  # P("4") = 0.1 (game_logic.py:114)
