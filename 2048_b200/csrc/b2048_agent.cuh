@@ -538,6 +538,236 @@ greedy_play_kernel(const float *__restrict__ w, const uint32_t *__restrict__ lut
     warp_add_counter(g.counters + B2048_CTR_ACTIVE, (in && d == 0 && !(flags & B2048_F_DONE)) ? 1u : 0u);
 }
 
+// ------------------------------------------------------------------------------------------------
+// sampled expectimax above the estimator: Game.look_forward (game_logic.py:214-243), estimator = evaluate.
+//   depth == 0 or empty_count >= since_empty  -> evaluate(afterstate)                           (:215-219)
+//   else sample min(width, empty) empty cells without replacement and a 2/4 tile for each      (:220-226),
+//        value = mean over them of max(0, game over ? -100 : max over changed directions of
+//        look_forward(afterstate', depth - 1))                                                 (:229-242)
+// The reference draws from Python's `random`; the device uses node-keyed Philox words (oracle_impl.h states the
+// spec: path code, purposes 2 / 3, the j-th position = the mulhi(word_j, left)-th remaining empty cell in row-major
+// order).  A direction that would create a 2^16 tile is skipped (reference undefined there).
+// Parallel shape: 16 lanes per root afterstate = (sampled tile j, direction d) of the first level; every lane walks
+// its subtree depth-first (template recursion on the remaining depth, one non-inlined body per level).
+// ------------------------------------------------------------------------------------------------
+struct LfParams {
+    uint64_t seed, id;
+    uint32_t move_no;
+    int width, since_empty;
+    uint32_t *evals;             // per-thread count of evaluate() calls (may be NULL)
+};
+
+template <int N>
+__device__ __forceinline__ float lf_leaf(const float *__restrict__ w, uint64_t b, const LfParams &P)
+{
+    if (P.evals) ++*P.evals;
+    return evaluate<N>(w, b);
+}
+
+template <int N, int D>
+__device__ __noinline__ float lf_node(const float *__restrict__ w, const uint32_t *__restrict__ lut, uint64_t b,
+                                      uint32_t path, LfParams P)
+{
+    if constexpr (D == 0) {
+        return lf_leaf<N>(w, b, P);
+    } else {
+        const uint64_t z = zero_nibbles(b);
+        const int empty = popc64(z);
+        if (empty >= P.since_empty) return lf_leaf<N>(w, b, P);
+        const int num = P.width < empty ? P.width : empty;
+        const Philox4 wp = spawn_words(P.seed, P.id, P.move_no, 2u | (path << 8));
+        const Philox4 wt = spawn_words(P.seed, P.id, P.move_no, 3u | (path << 8));
+        const uint32_t rp[4] = {wp.x, wp.y, wp.z, wp.w}, rt[4] = {wt.x, wt.y, wt.z, wt.w};
+        LutGlobal L{lut};
+        uint64_t left_mask = z;
+        float average = 0.0f;
+#pragma unroll 1
+        for (int j = 0; j < num; j++) {
+            const int sh = kth_empty_shift(left_mask, int(umulhi32(rp[j], uint32_t(empty - j))));
+            left_mask &= ~(1ULL << sh);                                     // without replacement
+            const uint64_t nb = b | (uint64_t(umulhi32(rt[j], 10u) == 0 ? 2u : 1u) << sh);
+            float best;
+            if (game_over(nb)) {
+                best = -100.0f;
+            } else {
+                best = -INFINITY;
+#pragma unroll 1
+                for (int d = 0; d < 4; d++) {
+                    uint32_t gain, fl;
+                    const uint64_t a = move_dir(L, nb, d, gain, fl);
+                    if ((fl & 3u) == 1u) {
+                        const float v = lf_node<N, D - 1>(w, lut, a, path * 16u + 4u * uint32_t(j) + uint32_t(d), P);
+                        if (v > best) best = v;
+                    }
+                }
+            }
+            average = __fadd_rn(average, best > 0.0f ? best : 0.0f);
+        }
+        return __fdiv_rn(average, float(num));
+    }
+}
+
+template <int N>
+__device__ __forceinline__ float lf_dispatch(const float *__restrict__ w, const uint32_t *__restrict__ lut, uint64_t b,
+                                             int depth, uint32_t path, const LfParams &P)
+{
+    switch (depth) {
+    case 0: return lf_node<N, 0>(w, lut, b, path, P);
+    case 1: return lf_node<N, 1>(w, lut, b, path, P);
+    case 2: return lf_node<N, 2>(w, lut, b, path, P);
+    default: return lf_node<N, 3>(w, lut, b, path, P);
+    }
+}
+
+constexpr int LF_MAX_DEPTH = 4;
+
+// look_forward value of one afterstate, computed by the 16 lanes `hmask` of a half-warp together (all of them
+// call with the same arguments; hl = lane index inside the half).  1 <= depth <= LF_MAX_DEPTH or 0.
+template <int N>
+__device__ __forceinline__ float lf_top(const float *__restrict__ w, const uint32_t *__restrict__ lut, uint64_t b, int depth,
+                                        uint32_t path, const LfParams &P, int hl, unsigned hmask)
+{
+    const uint64_t z = zero_nibbles(b);
+    const int empty = popc64(z);
+    if (depth == 0 || empty >= P.since_empty) {
+        if (P.evals && hl == 0) ++*P.evals;               // the 16 lanes compute the same value: counted once
+        return evaluate<N>(w, b);
+    }
+    const int num = P.width < empty ? P.width : empty;
+    const Philox4 wp = spawn_words(P.seed, P.id, P.move_no, 2u | (path << 8));
+    const Philox4 wt = spawn_words(P.seed, P.id, P.move_no, 3u | (path << 8));
+    const uint32_t rp[4] = {wp.x, wp.y, wp.z, wp.w}, rt[4] = {wt.x, wt.y, wt.z, wt.w};
+    const int j = hl >> 2, d = hl & 3;
+    uint64_t left_mask = z, nb = b;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        if (q < num) {
+            const int sh = kth_empty_shift(left_mask, int(umulhi32(rp[q], uint32_t(empty - q))));
+            left_mask &= ~(1ULL << sh);
+            if (q == j) nb = b | (uint64_t(umulhi32(rt[q], 10u) == 0 ? 2u : 1u) << sh);
+        }
+    }
+    const bool active = j < num;
+    const bool over = active && game_over(nb);
+    LutGlobal L{lut};
+    uint32_t gain, fl;
+    const uint64_t a = move_dir(L, nb, d, gain, fl);
+    float best = -INFINITY;
+    if (active && !over && (fl & 3u) == 1u) best = lf_dispatch<N>(w, lut, a, depth - 1, path * 16u + 4u * uint32_t(j) + uint32_t(d), P);
+    __syncwarp(hmask);
+    best = fmaxf(best, __shfl_xor_sync(hmask, best, 1, 16));
+    best = fmaxf(best, __shfl_xor_sync(hmask, best, 2, 16));
+    if (over) best = -100.0f;
+    const float c = best > 0.0f ? best : 0.0f;
+    float average = 0.0f;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const float cq = __shfl_sync(hmask, c, 4 * q, 16);
+        if (q < num) average = __fadd_rn(average, cq);
+    }
+    return __fdiv_rn(average, float(num));
+}
+
+// m afterstates, 16 lanes each
+template <int N>
+__global__ void __launch_bounds__(128)
+look_forward_kernel(const float *__restrict__ w, const uint32_t *__restrict__ lut, const uint64_t *__restrict__ boards,
+                    const uint64_t *__restrict__ game_id, const uint32_t *__restrict__ move_no,
+                    const uint8_t *__restrict__ root_dir, int64_t m, int depth, int width, int since_empty, uint64_t seed,
+                    float *__restrict__ value)
+{
+    const int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    const int64_t q = t >> 4;
+    const int hl = int(t & 15);
+    const unsigned hmask = 0xFFFFu << (threadIdx.x & 16);
+    if (q >= m) return;                                                   // uniform per half-warp
+    const LfParams P{seed, __ldg(game_id + q), __ldg(move_no + q), width, since_empty, nullptr};
+    const float v = lf_top<N>(w, lut, __ldg(boards + q), depth, 4u + uint32_t(__ldg(root_dir + q) & 3), P, hl, hmask);
+    if (hl == 0) value[q] = v;
+}
+
+// Game.trial_run with look-ahead (game_logic.py:150-183): one warp per game slot, the two half-warps score root
+// directions (0, 1) then (2, 3); strict '>' scanning d = 0..3, commit, Philox spawn.  Whole games per launch.
+template <int N>
+__global__ void __launch_bounds__(128)
+expectimax_play_kernel(const float *__restrict__ w, const uint32_t *__restrict__ lut, b2048_games_t g, int max_steps,
+                       int limit_tile, int step_limit, int depth, int width, int since_empty,
+                       int8_t *__restrict__ trace_dir, uint16_t *__restrict__ trace_spawn, int64_t trace_len)
+{
+    const int64_t slot = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31, half = lane >> 4, hl = lane & 15;
+    const unsigned hmask = 0xFFFFu << (lane & 16);
+    const bool in = slot < g.B;
+    LutGlobal L{lut};
+    uint64_t board = in ? g.board[slot] : 0;
+    uint32_t score = in ? g.score[slot] : 0;
+    uint32_t odo = in ? g.moves[slot] : 0;
+    uint32_t flags = in ? g.flags[slot] : B2048_F_DONE;
+    const uint64_t id = in ? g.game_id[slot] : 0;
+    bool run = in && !(flags & B2048_F_DONE);
+    uint32_t c_moves = 0, c_evals = 0;
+    for (int step = 0; step < max_steps && run; step++) {                 // warp-uniform: one game per warp
+        if (game_over(board) || (limit_tile && max_tile(board) >= limit_tile) || int(odo) >= step_limit) {
+            flags |= B2048_F_DONE;
+            break;
+        }
+        const LfParams P{g.seed, id, odo, width, since_empty, &c_evals};
+        float val[2];
+#pragma unroll
+        for (int pass = 0; pass < 2; pass++) {
+            const int rd = 2 * pass + half;
+            uint32_t gain, fl;
+            const uint64_t a = move_dir(L, board, rd, gain, fl);
+            val[pass] = (fl & 3u) == 1u ? lf_top<N>(w, lut, a, depth, 4u + uint32_t(rd), P, hl, hmask) : -INFINITY;
+            __syncwarp();
+        }
+        float v4[4];
+        v4[0] = __shfl_sync(FULL, val[0], 0);
+        v4[1] = __shfl_sync(FULL, val[0], 16);
+        v4[2] = __shfl_sync(FULL, val[1], 0);
+        v4[3] = __shfl_sync(FULL, val[1], 16);
+        int bd = -1;
+        float bv = -INFINITY;
+#pragma unroll
+        for (int d = 0; d < 4; d++)
+            if (v4[d] != -INFINITY || bd < 0) {
+                uint32_t gain, fl;
+                move_dir(L, board, d, gain, fl);
+                if ((fl & 3u) == 1u && (bd < 0 || v4[d] > bv)) { bd = d; bv = v4[d]; }
+            }
+        if (bd < 0) {                                                     // only 2^16-creating moves left: flag + stop
+            flags |= B2048_F_DONE | B2048_F_OVERFLOW;
+            break;
+        }
+        uint32_t gain, fl;
+        board = move_dir(L, board, bd, gain, fl);
+        score += gain;
+        if (lane == 0 && trace_dir && int64_t(odo) < trace_len) trace_dir[slot * trace_len + odo] = int8_t(bd);
+        odo++;
+        c_moves++;
+        const Philox4 r = spawn_words(g.seed, id, odo, 0u);
+        const uint32_t sp = spawn_apply(board, r.x, r.y);
+        if (lane == 0 && trace_spawn && int64_t(odo) <= trace_len) trace_spawn[slot * trace_len + odo - 1] = uint16_t(sp);
+    }
+    warp_add_counter(g.counters + B2048_CTR_EVALS, c_evals);
+    if (in && lane == 0) {
+        g.board[slot] = board;
+        g.score[slot] = score;
+        g.moves[slot] = odo;
+        g.flags[slot] = uint8_t(flags);
+        if (c_moves) atomicAdd(reinterpret_cast<unsigned long long *>(g.counters + B2048_CTR_MOVES), (unsigned long long)c_moves);
+        if (run && (flags & B2048_F_DONE)) {
+            atomicAdd(reinterpret_cast<unsigned long long *>(g.counters + B2048_CTR_FINISHED), 1ULL);
+            atomicAdd(reinterpret_cast<unsigned long long *>(g.counters + B2048_CTR_SCORE_SUM), (unsigned long long)score);
+            atomicAdd(reinterpret_cast<unsigned long long *>(g.counters + B2048_CTR_MOVES_SUM), (unsigned long long)odo);
+            if (flags & B2048_F_OVERFLOW) atomicAdd(reinterpret_cast<unsigned long long *>(g.counters + B2048_CTR_OVERFLOW), 1ULL);
+            atomicAdd(g.tile_hist + ((flags & B2048_F_OVERFLOW) ? 16 : max_tile(board)), 1u);
+            log_finished(g, id, score, odo, (flags & B2048_F_OVERFLOW) ? 16u : uint32_t(max_tile(board)), board);
+        }
+        if (!(flags & B2048_F_DONE)) atomicAdd(reinterpret_cast<unsigned long long *>(g.counters + B2048_CTR_ACTIVE), 1ULL);
+    }
+}
+
 // TD lock-step, phase A (see b2048.h).  4 lanes per slot (lane d = direction d); all 32 lanes of a warp must
 // call this together (width-4 shuffles inside).
 struct StepCounters {
@@ -1423,6 +1653,27 @@ int greedy_play_impl(const float *w, const uint32_t *lut, const b2048_games_t *g
     unsigned grid = unsigned(cdiv(g->B * 4, 128));
     greedy_play_kernel<N><<<grid, 128, 0, st>>>(w, lut, *g, max_steps, limit_tile, step_limit, rp, replay ? 1 : 0, trace_dir,
                                                trace_value, trace_spawn, trace_len);
+    return launch_status();
+}
+
+template <int N>
+int look_forward_impl(const float *w, const uint32_t *lut, const uint64_t *boards, const uint64_t *game_id,
+                      const uint32_t *move_no, const uint8_t *root_dir, int64_t m, int depth, int width, int since_empty,
+                      uint64_t seed, float *value, cudaStream_t st)
+{
+    look_forward_kernel<N><<<unsigned(cdiv(m * 16, 128)), 128, 0, st>>>(w, lut, boards, game_id, move_no, root_dir, m, depth,
+                                                                       width, since_empty, seed, value);
+    return launch_status();
+}
+
+template <int N>
+int expectimax_play_impl(const float *w, const uint32_t *lut, const b2048_games_t *g, int max_steps, int limit_tile,
+                         int step_limit, int depth, int width, int since_empty, int8_t *trace_dir, uint16_t *trace_spawn,
+                         int64_t trace_len, cudaStream_t st)
+{
+    expectimax_play_kernel<N><<<unsigned(cdiv(g->B * 32, 128)), 128, 0, st>>>(w, lut, *g, max_steps, limit_tile, step_limit,
+                                                                             depth, width, since_empty, trace_dir,
+                                                                             trace_spawn, trace_len);
     return launch_status();
 }
 

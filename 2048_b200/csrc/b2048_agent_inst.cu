@@ -10,4 +10,5 @@
 extern const b2048_agent_ops B2048_CAT(b2048_agent_ops_, B2048_N) = {
     features_impl<B2048_N>,  evaluate_impl<B2048_N>,   td_update_impl<B2048_N>,
     greedy_play_impl<B2048_N>, td_phase_a_impl<B2048_N>, td_run_persistent<B2048_N>,
+    look_forward_impl<B2048_N>, expectimax_play_impl<B2048_N>,
 };

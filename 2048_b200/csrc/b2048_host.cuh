@@ -145,6 +145,12 @@ struct b2048_agent_ops {
     int (*td_run_persistent)(float *w, float *delta, const uint32_t *lut, const b2048_games_t *g, float alpha, int mode,
                              int steps, uint64_t *upd_board, float *upd_dw, void *work, size_t work_bytes,
                              cudaStream_t st);
+    int (*look_forward)(const float *w, const uint32_t *lut, const uint64_t *boards, const uint64_t *game_id,
+                        const uint32_t *move_no, const uint8_t *root_dir, int64_t m, int depth, int width,
+                        int since_empty, uint64_t seed, float *value, cudaStream_t st);
+    int (*expectimax_play)(const float *w, const uint32_t *lut, const b2048_games_t *g, int max_steps, int limit_tile,
+                           int step_limit, int depth, int width, int since_empty, int8_t *trace_dir,
+                           uint16_t *trace_spawn, int64_t trace_len, cudaStream_t st);
 };
 extern const b2048_agent_ops b2048_agent_ops_2, b2048_agent_ops_3, b2048_agent_ops_4, b2048_agent_ops_5,
     b2048_agent_ops_6;

@@ -463,6 +463,32 @@ int b2048_greedy_play(int n, const float *weights, const uint32_t *lut, const b2
                                      trace_spawn, trace_len, S(stream));
 }
 
+int b2048_look_forward(int n, const float *weights, const uint32_t *lut, const uint64_t *boards, const uint64_t *game_id,
+                       const uint32_t *move_no, const uint8_t *root_dir, int64_t m, int depth, int width, int since_empty,
+                       uint64_t seed, float *value, b2048_stream_t stream)
+{
+    if (m < 0 || num_feat(n) < 0 || !weights || !lut || depth < 0 || depth > 4 || width < 1 || width > 4 || since_empty < 0 ||
+        (m && (!boards || !game_id || !move_no || !root_dir || !value)))
+        return B2048_EINVAL;
+    if (!m) return 0;
+    return agent_ops(n)->look_forward(weights, lut, boards, game_id, move_no, root_dir, m, depth, width, since_empty, seed,
+                                      value, S(stream));
+}
+
+int b2048_expectimax_play(int n, const float *weights, const uint32_t *lut, const b2048_games_t *g, int max_steps,
+                          int limit_tile, int step_limit, int depth, int width, int since_empty, int8_t *trace_dir,
+                          uint16_t *trace_spawn, int64_t trace_len, b2048_stream_t stream)
+{
+    if (!games_ok(g) || num_feat(n) < 0 || !weights || !lut || max_steps < 0 || depth < 0 || depth > 4 || width < 1 ||
+        width > 4 || since_empty < 0)
+        return B2048_EINVAL;
+    if (g->B == 0) return 0;
+    cudaError_t e = cudaMemsetAsync(g->counters + B2048_CTR_ACTIVE, 0, sizeof(uint64_t), S(stream));
+    if (e != cudaSuccess) return int(e);
+    return agent_ops(n)->expectimax_play(weights, lut, g, max_steps, limit_tile, step_limit, depth, width, since_empty,
+                                         trace_dir, trace_spawn, trace_len, S(stream));
+}
+
 int b2048_td_phase_a(int n, const float *weights, const uint32_t *lut, const b2048_games_t *g, float alpha,
                      uint64_t *upd_board, float *upd_dw, const b2048_replay_t *replay, int8_t *trace_dir,
                      float *trace_value, float *trace_dw, uint16_t *trace_spawn, int64_t trace_len,

@@ -65,6 +65,8 @@ SIGNATURES = {
     "b2048_td_phase_a": (_int, [_int, _vp, _vp, _GP, _f32, _vp, _vp, _RP, _vp, _vp, _vp, _vp, _i64, _vp]),
     "b2048_td_run": (_int, [_int, _vp, _vp, _vp, _GP, _f32, _int, _int, _vp, _vp, _vp, _sz, _vp]),
     "b2048_td_run_launches": (_i64, [_int, _i64, _int, _int]),
+    "b2048_look_forward": (_int, [_int, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _int, _u64, _vp, _vp]),
+    "b2048_expectimax_play": (_int, [_int, _vp, _vp, _GP, _int, _int, _int, _int, _int, _int, _vp, _vp, _i64, _vp]),
     "b2048_delta_pack": (_int, [_vp, _vp, _i64, _vp]),
     "b2048_delta_pack_diff": (_int, [_vp, _vp, _vp, _i64, _vp]),
     "b2048_delta_apply": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp]),

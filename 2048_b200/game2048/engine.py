@@ -143,6 +143,16 @@ class Context:
         check(self.lib.b2048_evaluate(n, dptr(weights), dptr(boards), m, dptr(out), cur_stream()), "evaluate")
         return out
 
+    def look_forward(self, n, weights, boards, game_id, move_no, root_dir, depth, width=1, since_empty=6, seed=0):
+        """Game.look_forward (game_logic.py:214-243) values of m afterstates (device tensors: boards int64 bits,
+        game_id int64, move_no int32, root_dir uint8) -> float32 [m]"""
+        m = boards.shape[0]
+        out = self.empty(m, F32)
+        check(self.lib.b2048_look_forward(n, dptr(weights), dptr(self.lut), dptr(boards), dptr(game_id), dptr(move_no),
+                                          dptr(root_dir), m, int(depth), int(width), int(since_empty), int(seed), dptr(out),
+                                          cur_stream()), "look_forward")
+        return out
+
     def update_workspace(self, n, m, mode):
         nbytes = self.lib.b2048_td_update_workspace(n, m, mode)
         return self.zeros(max(nbytes, 16), U8)
@@ -271,6 +281,24 @@ def greedy_play(ctx, n, weights, games, limit_tile=0, step_limit=100000, chunk=2
         if active == 0 or replay is not None or (max_launches and launches >= max_launches):
             break
     return tdir, tval, tsp
+
+
+def expectimax_play(ctx, n, weights, games, depth, width=1, since_empty=6, limit_tile=0, step_limit=100000, chunk=256,
+                    max_launches=None, trace_len=0):
+    """Game.trial_run with look-ahead (depth / width / since_empty, game_logic.py:150-183, 214-243) for every slot
+    until all are done; one warp per game, whole games on the device.
+    Returns (trace_dir, None, trace_spawn) like greedy_play (None when trace_len == 0)."""
+    tdir = ctx.empty((games.B, trace_len), torch.int8).fill_(-2) if trace_len else None
+    tsp = ctx.zeros((games.B, trace_len), torch.int16) if trace_len else None
+    launches = 0
+    while True:
+        check(ctx.lib.b2048_expectimax_play(n, dptr(weights), dptr(ctx.lut), C.byref(games.c), chunk, limit_tile, step_limit,
+                                            int(depth), int(width), int(since_empty), dptr(tdir), dptr(tsp), trace_len,
+                                            cur_stream()), "expectimax_play")
+        launches += 1
+        if int(games.counters[cabi.CTR_ACTIVE].item()) == 0 or (max_launches and launches >= max_launches):
+            break
+    return tdir, None, tsp
 
 
 class TDTrainer:

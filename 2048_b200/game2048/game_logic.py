@@ -200,12 +200,30 @@ class Game:
     def _find_best_move(self, estimator, depth, width, since_empty):
         best_dir, best_value = 0, -np.inf
         best_row, best_score = None, None
-        for direction in range(4):
-            new_row, new_score, change = self.pre_move(self.row, self.score, direction)
+        agent = self._agent_of(estimator) if depth > 0 else None
+        cand = [(d,) + tuple(self.pre_move(self.row, self.score, d)) for d in range(4)]
+        device_values = {}
+        if agent is not None and 1 <= width <= 4 and depth <= 4:
+            # all look_forward trees of the move in one kernel (b2048_look_forward, node-keyed Philox draws);
+            # other estimators / parameters keep the reference's host recursion on Python's `random`
+            ctx = engine.Context.get()
+            valid = [c for c in cand if c[3]]
+            if valid:
+                if not hasattr(self, '_lf_seed'):
+                    self._lf_seed = random.getrandbits(63)
+                boards = ctx.to_device(np.array([pack_row(c[1]) for c in valid], dtype=np.uint64))
+                k = len(valid)
+                vals = ctx.look_forward(agent.n, agent._device_weights(), boards,
+                                        ctx.to_device(np.zeros(k, dtype=np.uint64)),
+                                        ctx.to_device(np.full(k, self.odometer, dtype=np.uint32)),
+                                        ctx.to_device(np.array([c[0] for c in valid], dtype=np.uint8)), depth, width,
+                                        since_empty, seed=self._lf_seed).cpu().numpy()
+                device_values = {c[0]: float(v) for c, v in zip(valid, vals)}
+        for direction, new_row, new_score, change in cand:
             if not change:
                 continue
-            value = self.look_forward(estimator, new_row, new_score, depth=depth, width=width,
-                                      since_empty=since_empty)
+            value = device_values[direction] if direction in device_values else \
+                self.look_forward(estimator, new_row, new_score, depth=depth, width=width, since_empty=since_empty)
             if value > best_value:                           # strict: the lowest direction wins ties
                 best_dir, best_value = direction, value
                 best_row, best_score = new_row, new_score

@@ -374,8 +374,8 @@ class QAgent:
         start = benchmark_time = time.time()
         counter0 = Game.counter
         results = []
-        if agent is not None and depth == 0 and not verbose and not stopper:
-            results = QAgent._trial_device(agent, num, limit_tile, game_init, seed, display)
+        if agent is not None and not verbose and not stopper and depth <= 4 and (depth == 0 or 1 <= width <= 4):
+            results = QAgent._trial_device(agent, num, limit_tile, game_init, seed, display, depth, width, since_empty)
         else:
             for i in range(num):
                 if stopper:
@@ -423,9 +423,15 @@ class QAgent:
         return results
 
     @staticmethod
-    def _trial_device(agent, num, limit_tile, game_init, seed, display):
-        """all `num` games in one batch (b2048_greedy_play); the best game is replayed once with tracing so that
-        its moves / tiles can be saved and replayed like a reference game"""
+    def _trial_device(agent, num, limit_tile, game_init, seed, display, depth=0, width=1, since_empty=6):
+        """all `num` games in one batch (b2048_greedy_play, or b2048_expectimax_play when depth > 0); the best game
+        is replayed once with tracing so that its moves / tiles can be saved and replayed like a reference game"""
+        def play(games, **kw):
+            if depth == 0:
+                return engine.greedy_play(ctx, agent.n, agent._device_weights(), games, limit_tile=limit_tile, **kw)
+            return engine.expectimax_play(ctx, agent.n, agent._device_weights(), games, depth, width, since_empty,
+                                          limit_tile=limit_tile, **kw)
+
         ctx = engine.Context.get()
         seed = random.getrandbits(63) if seed is None else int(seed)
         games = engine.GameBatch(num, seed=seed, ctx=ctx).init(first_id=0)
@@ -433,7 +439,7 @@ class QAgent:
             games.set_positions(np.full(num, pack_row(game_init.row), dtype=np.uint64), [game_init.score] * num)
             games.game_id.copy_(ctx.to_device(np.arange(num, dtype=np.uint64)))
         starts = games.to_host()['board'].copy()
-        engine.greedy_play(ctx, agent.n, agent._device_weights(), games, limit_tile=limit_tile)
+        play(games)
         h = games.to_host()
         c = games.read_counters()
         Game.counter += 4 * c['moves']                               # pre_move calls the reference would have made
@@ -449,7 +455,7 @@ class QAgent:
         one.set_positions(starts[best:best + 1], None if game_init is None else [game_init.score])
         one.game_id.fill_(best)
         L = int(h['moves'][best]) + 1
-        tdir, _, tsp = engine.greedy_play(ctx, agent.n, agent._device_weights(), one, limit_tile=limit_tile, trace_len=L)
+        tdir, _, tsp = play(one, trace_len=L)
         results[best].adopt_device_result(one.to_host(), 0, tdir, tsp)
         for j, g in enumerate(results):
             display(f'game {j}, result {g.score}, moves {g.odometer}, achieved {1 << np.max(g.row)}')

@@ -34,7 +34,10 @@ def parse():
     p.add_argument("--steps", type=int, default=20)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    p.add_argument("--workload", default="td", choices=["td", "greedy", "sweep"])
+    p.add_argument("--workload", default="td", choices=["td", "greedy", "sweep", "expectimax"])
+    p.add_argument("--depth", type=int, default=3, help="expectimax: look-ahead depth (the reference's best: 3)")
+    p.add_argument("--width", type=int, default=4, help="expectimax: sampled tiles per node")
+    p.add_argument("--since-empty", type=int, default=6, help="expectimax: look ahead only below this many empty cells")
     p.add_argument("--n", type=int, default=4)
     p.add_argument("--games", type=int, default=4096, help="game slots per GPU")
     p.add_argument("--lock-steps", type=int, default=2048, help="lock-steps per bench step (td)")
@@ -456,11 +459,16 @@ def run_greedy(args):
     flush = ctx.zeros(64 << 20, torch.int32)
     score_host, moves_host = torch.empty(B, dtype=torch.int32).pin_memory(), torch.empty(B, dtype=torch.int32).pin_memory()
 
+    look = args.workload == "expectimax"
+
     def step(e2e=False):
         if e2e:
             wd.copy_(w_host, non_blocking=True)
         games.init(first_id=rank * B)
-        engine.greedy_play(ctx, n, wd, games, chunk=args.chunk)
+        if look:
+            engine.expectimax_play(ctx, n, wd, games, args.depth, args.width, args.since_empty, chunk=args.chunk)
+        else:
+            engine.greedy_play(ctx, n, wd, games, chunk=args.chunk)
         if e2e:                                                  # per-game result: score, moves (+ counters)
             score_host.copy_(games.score, non_blocking=True)
             moves_host.copy_(games.moves, non_blocking=True)
@@ -492,6 +500,7 @@ def run_greedy(args):
         ms += a.elapsed_time(b)
         c = games.read_counters()
         moves += c["moves"]; evals += c["evals"]
+        score_avg = c["score_sum"] / max(c["finished"], 1)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     e_ms, e_moves = 0.0, 0
@@ -515,21 +524,29 @@ def run_greedy(args):
         value = moves / (ms * 1e-3)
         ach = value / world * bpm / 1e9
         sector = value / world * (16 + 32 * F * E) / 1e9
-        line = {"metric": "greedy_moves_per_sec", "value": value, "unit": "moves/s", "n_gpus": world, "steps": args.steps,
+        line = {"metric": "expectimax_moves_per_sec" if look else "greedy_moves_per_sec", "value": value, "unit": "moves/s",
+                "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"BASELINE configs[3] shape: Q_agent n={n} greedy play of {B} seeded games per GPU to "
-                                       f"completion, seeded random-init weights" + (f" + {args.pretrain} TD lock-steps" if args.pretrain else ""),
+                "config": {"workload": (f"SURVEY 8(f) rank 1: Q_agent n={n} play with look-ahead depth={args.depth} width={args.width} "
+                                        f"since_empty={args.since_empty} (game_logic.py:214-243), {B} seeded games per GPU to completion"
+                                        if look else
+                                        f"BASELINE configs[3] shape: Q_agent n={n} greedy play of {B} seeded games per GPU to "
+                                        f"completion") + ", seeded random-init weights" +
+                                       (f" + {args.pretrain} TD lock-steps" if args.pretrain else ""),
                            "n": n, "games_per_gpu": B, "moves_per_game": moves / world / args.steps / B,
+                           "avg_score_rank0": score_avg,
                            "l2": "a 256 MiB buffer is written between timed steps to flush L2"},
                 "clocks": clocks,
                 "e2e": {"value": e_moves / (e_ms * 1e-3), "unit": "moves/s", "h2d_bytes_per_step": wd.numel() * 4,
                         "d2h_bytes_per_step": B * 8 + cabi.CTR_COUNT * 8},
                 "gpu_launches": None,
-                "roofline": {"bound": "hbm", "kernel": "greedy_play_kernel (4 LUT moves, F-table gather per valid afterstate, "
+                "roofline": {"bound": "hbm", "kernel": "expectimax_play_kernel (one warp per game, 16 lanes per root afterstate, "
+                                                       "depth-first subtrees, F-table gather per leaf)" if look else
+                                                       "greedy_play_kernel (4 LUT moves, F-table gather per valid afterstate, "
                                                        "argmax, Philox spawn; whole games per launch)",
                              "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                             "traffic": (lambda t: t * moves / world / args.steps if t and n == 6 and not args.pretrain else None)(
+                             "traffic": (lambda t: t * moves / world / args.steps if t and n == 6 and not args.pretrain and not look else None)(
                                  ncu_traffic("greedy_n6_B131072_random_init", "bytes_per_move")),
                              "peak_source": how, "bytes_per_move": bpm, "evals_per_move": E,
                              "sector_granular_GBps": sector,
@@ -540,10 +557,14 @@ def run_greedy(args):
             from oracle import oracle as orc
             orc.build()
             t0 = time.perf_counter()
-            r = orc.play_philox(n, w_host.numpy(), seed=0, first_id=0, num=min(B, args.cpu_games), threads=orc.max_threads())
+            if look:
+                r = orc.play_expectimax(n, w_host.numpy(), 0, 0, min(B, max(orc.max_threads(), 8)), args.depth, args.width,
+                                        args.since_empty, threads=orc.max_threads())
+            else:
+                r = orc.play_philox(n, w_host.numpy(), seed=0, first_id=0, num=min(B, args.cpu_games), threads=orc.max_threads())
             dt = time.perf_counter() - t0
             line["cpu_baseline"] = {"value": r["total_moves"] / dt, "unit": "moves/s", "cores": orc.max_threads(), "kind": "port",
-                                    "sample": f"{min(B, args.cpu_games)} of the same games ({dt:.1f} s)"}
+                                    "sample": f"{len(r['scores'])} of the same games ({dt:.1f} s)"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -649,12 +670,19 @@ def main():
         args.n = 6
     if args.workload == "greedy" and "--games" not in sys.argv:
         args.games = 131072
+    if args.workload == "expectimax":
+        if "--games" not in sys.argv:
+            args.games = 1024
+        if "--pretrain" not in sys.argv:
+            args.pretrain = 3000
+        if "--chunk" not in sys.argv:
+            args.chunk = 256
     if args.impl == "reference":
         if args.workload != "td":
             raise SystemExit("--impl reference is the td workload (the headline); greedy / sweep lines carry cpu_baseline")
         run_reference(args)
         return
-    {"td": run_td, "greedy": run_greedy, "sweep": run_sweep}[args.workload](args)
+    {"td": run_td, "greedy": run_greedy, "sweep": run_sweep, "expectimax": run_greedy}[args.workload](args)
 
 
 if __name__ == "__main__":

@@ -193,6 +193,26 @@ int b2048_greedy_play(int n, const float *weights, const uint32_t *lut, const b2
                       int limit_tile, int step_limit, const b2048_replay_t *replay, int8_t *trace_dir,
                       float *trace_value, uint16_t *trace_spawn, int64_t trace_len, b2048_stream_t stream);
 
+/* Game.look_forward, game_logic.py:214-243, with estimator = QAgent.evaluate, for m afterstates: the sampled
+ * expectimax of the reference (depth 0..4, width 1..4, since_empty as there; a leaf or a node with
+ * empty_count >= since_empty is evaluate(); otherwise min(width, empty) empty cells are sampled without
+ * replacement with a 2/4 tile each, and the value is the mean of max(0, game over ? -100 : best direction)).
+ * The reference draws from Python's `random`; here every node draws node-keyed Philox words: key = seed, counter =
+ * (id_lo, id_hi, move_no, purpose | path << 8), purpose 2 = positions, 3 = tiles, path = 4 + root_dir at the root
+ * afterstate and path * 16 + 4 * tile_index + direction below it.  root_dir[q] = the direction that produced
+ * afterstate q.  16 lanes per afterstate.  A direction that would create a 2^16 tile is skipped. */
+int b2048_look_forward(int n, const float *weights, const uint32_t *lut, const uint64_t *boards, const uint64_t *game_id,
+                       const uint32_t *move_no, const uint8_t *root_dir, int64_t m, int depth, int width, int since_empty,
+                       uint64_t seed, float *value, b2048_stream_t stream);
+/* Game.trial_run with look-ahead, game_logic.py:150-183 (_find_best_move above look_forward, strict '>' over
+ * d = 0..3, commit, Philox spawn) for every slot that is not DONE, up to max_steps moves per slot in one launch,
+ * one warp per game; move_no of a node = the slot's odometer before the move.  Counters as b2048_greedy_play
+ * (B2048_CTR_EVALS counts the evaluate() calls at the leaves and cut-offs of the trees); trace_dir / trace_spawn
+ * [B, trace_len] as there (may be NULL). */
+int b2048_expectimax_play(int n, const float *weights, const uint32_t *lut, const b2048_games_t *g, int max_steps,
+                          int limit_tile, int step_limit, int depth, int width, int since_empty, int8_t *trace_dir,
+                          uint16_t *trace_spawn, int64_t trace_len, b2048_stream_t stream);
+
 /* One lock-step of QAgent.episode (r_learning.py:224-252) for all B slots, two launches:
  *   phase A (every slot, weights W_t read-only): game over -> terminal dw = -old_label*alpha/F
  *     (:247-249), statistics, in-place restart; else best afterstate by strict '>' over d=0..3

@@ -90,6 +90,13 @@ def _declare(L):
         f.argtypes = [C.c_int, rp, C.c_uint64, C.c_uint64, C.c_int64, C.c_int, C.c_int, C.c_int,
                       i64p, i32p, i32p, u64p, i64p]
         f.restype = C.c_int64
+        f = getattr(L, "orc_look_forward_" + suf)
+        f.argtypes = [C.c_int, rp, i32p, i64p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, i32p, C.c_int64, i32p,
+                      C.c_int64, C.c_uint64, u64p, u32p, i32p, rp]
+        f = getattr(L, "orc_play_expectimax_" + suf)
+        f.argtypes = [C.c_int, rp, C.c_uint64, C.c_uint64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                      i64p, i32p, u64p]
+        f.restype = C.c_int64
         f = getattr(L, "orc_td_lockstep_" + suf)
         f.argtypes = [C.c_int, rp, rt, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int,
                       C.c_int, u64p, i64p, i32p, u64p, u64p, rp, u8p, i64p, i64p, i64p, i32p, i64p]
@@ -283,6 +290,43 @@ def play_philox(n, w, seed, first_id, num, limit_tile=0, step_limit=100000, thre
         n, _p(w, ct), seed, first_id, num, limit_tile, step_limit, threads, _p(scores, C.c_int64),
         _p(nm, C.c_int32), _p(mt, C.c_int32), _p(fb, C.c_uint64), _p(ne, C.c_int64))
     return dict(total_moves=int(total), scores=scores, moves=nm, max_tile=mt, boards=fb, n_eval=int(ne[0]))
+
+
+def look_forward(n, w, rows, scores, depth, width, since_empty, log=None, seed=0, ids=None, move_no=None,
+                 root_dir=None):
+    """Game.look_forward (game_logic.py:214-243) with estimator = evaluate, for m afterstates.
+    log = (positions, tiles): replay the reference's logged random.sample / randrange results (depth-first order);
+    otherwise the Philox node-keyed spec with per-afterstate ids / move_no / root_dir."""
+    suf, ct = _real(w.dtype)
+    r = _rows(rows)
+    m = r.shape[0]
+    sc = np.ascontiguousarray(scores, dtype=np.int64) if scores is not None else np.zeros(m, np.int64)
+    out = np.zeros(m, w.dtype)
+    if log is not None:
+        lp, lt = (np.ascontiguousarray(x, dtype=np.int32) for x in log)
+        rc = getattr(lib(), "orc_look_forward_" + suf)(n, _p(w, ct), _p(r, C.c_int32), _p(sc, C.c_int64), m, depth, width,
+                                                       since_empty, 1, _p(lp, C.c_int32), len(lp), _p(lt, C.c_int32),
+                                                       len(lt), 0, None, None, None, _p(out, ct))
+    else:
+        idv = np.ascontiguousarray(ids, dtype=np.uint64)
+        mv = np.ascontiguousarray(move_no, dtype=np.uint32)
+        rd = np.ascontiguousarray(root_dir, dtype=np.int32)
+        rc = getattr(lib(), "orc_look_forward_" + suf)(n, _p(w, ct), _p(r, C.c_int32), _p(sc, C.c_int64), m, depth, width,
+                                                       since_empty, 0, None, 0, None, 0, seed, _p(idv, C.c_uint64),
+                                                       _p(mv, C.c_uint32), _p(rd, C.c_int32), _p(out, ct))
+    if rc:
+        raise RuntimeError(f"orc_look_forward failed: {rc}")
+    return out
+
+
+def play_expectimax(n, w, seed, first_id, num, depth, width, since_empty, limit_tile=0, step_limit=100000, threads=0):
+    """trial_run with look-ahead (game_logic.py:150-183, 214-243) on the Philox streams, games [first_id, +num)"""
+    suf, ct = _real(w.dtype)
+    scores, nm, fb = np.zeros(num, np.int64), np.zeros(num, np.int32), np.zeros(num, np.uint64)
+    total = getattr(lib(), "orc_play_expectimax_" + suf)(n, _p(w, ct), seed, first_id, num, depth, width, since_empty,
+                                                         limit_tile, step_limit, threads, _p(scores, C.c_int64),
+                                                         _p(nm, C.c_int32), _p(fb, C.c_uint64))
+    return dict(total_moves=int(total), scores=scores, moves=nm, boards=fb)
 
 
 class LockStep:

@@ -253,6 +253,159 @@ int64_t FN(orc_play_philox)(int n, const REAL *w, uint64_t seed, uint64_t first_
 }
 
 /*
+ * game_logic.py:214-243  Game.look_forward: the sampled expectimax above the estimator, with
+ * estimator = QAgent.evaluate.  Statement by statement:
+ *   :215-216  depth == 0                      -> evaluate(row)
+ *   :217-219  empty_count(row) >= since_empty -> evaluate(row)
+ *   :220-222  num_tiles = min(width, empty);  tile_positions = random.sample(empty cells, num_tiles)
+ *   :226      new_tile = 1 if random.randrange(10) else 2          (drawn per position, in loop order)
+ *   :229-231  game over after the spawn       -> best_value = -100
+ *   :233-239  else max over the changed directions of look_forward(afterstate, depth - 1)
+ *   :241-242  average += max(best_value, 0);  return average / num_tiles
+ * Randomness comes from an orc_lf_rng:
+ *   replay mode (pinning against the real reference): the logged results of random.sample /
+ *     random.randrange, consumed in the reference's depth-first call order;
+ *   Philox mode (the device's spec): node-keyed words.  A node's path code starts at 4 + root direction and
+ *     becomes path * 16 + 4 * t + d going down through sampled tile t and direction d; positions come from
+ *     counter (id_lo, id_hi, move_no, 2 | path << 8): the j-th position is the mulhi(word_j, left)-th of the
+ *     `left` = empty - j empty cells not yet taken (row-major order); tiles from counter (.., 3 | path << 8):
+ *     "4" iff mulhi(word_j, 10) == 0.  width <= 4.
+ */
+typedef struct {
+    int replay;                  /* 1: consume logs; 0: Philox */
+    const int32_t *log_pos;      /* flat positions, in draw order */
+    const int32_t *log_tile;     /* tiles (1 | 2), in draw order */
+    int64_t n_pos, n_tile, i_pos, i_tile;
+    uint64_t seed, id;
+    uint32_t move_no;
+} FN(orc_lf_rng);
+
+static REAL FN(look_forward_rec)(int n, const REAL *w, const int32_t *row, int64_t score, int depth, int width,
+                                 int since_empty, FN(orc_lf_rng) *rng, uint32_t path, int *err)
+{
+    if (depth == 0) return FN(orc_evaluate)(n, w, row);
+    int32_t cells[16];
+    int empty = orc_empty(row, cells);
+    if (empty >= since_empty) return FN(orc_evaluate)(n, w, row);
+    int num = width < empty ? width : empty;
+    int32_t pos[4];
+    int32_t tile[4];
+    if (num > 4) { *err = 1; return 0; }
+    if (rng->replay) {
+        if (rng->i_pos + num > rng->n_pos) { *err = 2; return 0; }
+        for (int j = 0; j < num; j++) pos[j] = rng->log_pos[rng->i_pos++];
+    } else {
+        uint32_t wp[4], wt[4];
+        orc_spawn_words(rng->seed, rng->id, rng->move_no, 2u | (path << 8), wp);
+        orc_spawn_words(rng->seed, rng->id, rng->move_no, 3u | (path << 8), wt);
+        int left = empty;
+        for (int j = 0; j < num; j++, left--) {
+            int k = (int)mulhi32(wp[j], (uint32_t)left);
+            pos[j] = cells[k];
+            for (int q = k; q + 1 < left; q++) cells[q] = cells[q + 1];     /* without replacement */
+            tile[j] = mulhi32(wt[j], 10u) == 0 ? 2 : 1;
+        }
+    }
+    REAL average = 0;
+    for (int j = 0; j < num; j++) {
+        if (rng->replay) {
+            if (rng->i_tile >= rng->n_tile) { *err = 2; return 0; }
+            tile[j] = rng->log_tile[rng->i_tile++];
+        }
+        int32_t nr[16];
+        memcpy(nr, row, sizeof nr);
+        nr[pos[j]] = tile[j];
+        REAL best;
+        if (orc_game_over(nr)) {
+            best = -100;
+        } else {
+            best = -INFINITY;
+            for (int d = 0; d < 4; d++) {
+                int32_t tr[16];
+                int64_t ts;
+                int ch = orc_pre_move(nr, score, d, tr, &ts);
+                if (ch < 0) { *err = 3; return 0; }                       /* the reference's KeyError */
+                if (ch && orc_max_tile(tr) > 15) ch = 0;   /* 2^16 escape: the reference is undefined there; skipped */
+                if (ch) {
+                    REAL v = FN(look_forward_rec)(n, w, tr, ts, depth - 1, width, since_empty, rng,
+                                                  path * 16u + 4u * (uint32_t)j + (uint32_t)d, err);
+                    if (v > best) best = v;
+                }
+            }
+        }
+        average = average + (best > 0 ? best : 0);
+    }
+    return average / (REAL)num;
+}
+
+/* game_logic.py:150-161 _find_best_move above look_forward, then trial_run (:170-183) with the Philox spawn
+ * stream: games [first_id, first_id + num) played with depth / width / since_empty look-ahead (the device's
+ * b2048_expectimax_play).  A direction whose afterstate holds a 2^16 tile is skipped. */
+int64_t FN(orc_play_expectimax)(int n, const REAL *w, uint64_t seed, uint64_t first_id, int64_t num, int depth, int width,
+                                int since_empty, int limit_tile, int step_limit, int threads, int64_t *scores,
+                                int32_t *n_moves, uint64_t *final_board)
+{
+    int64_t total_moves = 0;
+#ifdef _OPENMP
+    if (threads <= 0) threads = omp_get_max_threads();
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads) reduction(+ : total_moves)
+#endif
+    for (int64_t g = 0; g < num; g++) {
+        int32_t row[16];
+        int64_t score = 0;
+        int odo = 0;
+        uint64_t id = first_id + (uint64_t)g;
+        orc_spawn_initial(seed, id, row);
+        while (odo < step_limit) {
+            if (orc_game_over(row)) break;
+            if (limit_tile && orc_max_tile(row) >= limit_tile) break;
+            int best_dir = -1, err = 0;
+            int32_t best_row[16];
+            int64_t best_score = 0;
+            REAL best_value = -INFINITY;
+            FN(orc_lf_rng) rng = {0, NULL, NULL, 0, 0, 0, 0, seed, id, (uint32_t)odo};
+            for (int d = 0; d < 4; d++) {
+                int32_t nr[16];
+                int64_t ns;
+                int ch = orc_pre_move(row, score, d, nr, &ns);
+                if (ch <= 0 || orc_max_tile(nr) > 15) continue;
+                REAL v = FN(look_forward_rec)(n, w, nr, ns, depth, width, since_empty, &rng, 4u + (uint32_t)d, &err);
+                if (v > best_value || best_dir < 0) {               /* :157 strict '>', first valid direction wins ties */
+                    if (best_dir < 0 || v > best_value) { best_value = v; best_dir = d; memcpy(best_row, nr, sizeof nr); best_score = ns; }
+                }
+            }
+            if (best_dir < 0 || err) break;
+            memcpy(row, best_row, sizeof row);
+            score = best_score;
+            odo++;
+            orc_spawn_move(seed, id, (uint32_t)odo, row);
+        }
+        total_moves += odo;
+        if (scores) scores[g] = score;
+        if (n_moves) n_moves[g] = odo;
+        if (final_board) final_board[g] = orc_pack(row);
+    }
+    return total_moves;
+}
+
+/* look_forward values of m afterstates (rows [m,16]); Philox mode: root_dir[q] = the direction that produced
+ * afterstate q (path code 4 + dir), ids/move_no per afterstate.  Returns 0, or an error code. */
+int FN(orc_look_forward)(int n, const REAL *w, const int32_t *rows, const int64_t *scores, int64_t m, int depth,
+                         int width, int since_empty, int replay, const int32_t *log_pos, int64_t n_pos,
+                         const int32_t *log_tile, int64_t n_tile, uint64_t seed, const uint64_t *ids,
+                         const uint32_t *move_no, const int32_t *root_dir, REAL *values)
+{
+    FN(orc_lf_rng) rng = {replay, log_pos, log_tile, n_pos, n_tile, 0, 0, seed, 0, 0};
+    int err = 0;
+    for (int64_t q = 0; q < m && !err; q++) {
+        if (!replay) { rng.id = ids[q]; rng.move_no = move_no[q]; }
+        values[q] = FN(look_forward_rec)(n, w, rows + 16 * q, scores ? scores[q] : 0, depth, width, since_empty,
+                                         &rng, 4u + (uint32_t)(replay ? 0 : root_dir[q]), &err);
+    }
+    return err;
+}
+
+/*
  * update() for m (board, dw) entries sharing one table set -- the restatement b2048_td_update is
  * checked against.  Entries with NaN dw are skipped.  rule:
  *   0 : w[k] += dw one contribution at a time, entry order, reference key order (QAgent.update x m)

@@ -136,3 +136,28 @@ def test_trial_and_train_run_drivers(mods, fx, tmp_path, monkeypatch, capsys):
     assert third.alpha == agent.alpha and torch.equal(third._device_weights(), agent._device_weights())
     row = results[0].row
     assert third.evaluate(row) == agent.evaluate(row)
+
+
+def test_look_ahead_drivers(mods, fx, capsys):
+    """trial / trial_run with depth > 0 (game_logic.py:150-183, 214-243): the batched device expectimax plays
+    better than depth 0 from the same weights, its best game replays, and a single Game.trial_run(depth=2) with the
+    agent's estimator runs its look_forward trees on the device"""
+    gl, rl = mods
+    np.random.seed(1)
+    random.seed(1)
+    agent = rl.QAgent(name="la", storage="local", console="local", n=4, batch=256)
+    agent.train_run(num_eps=600, saving=False)
+    capsys.readouterr()
+    r0 = rl.QAgent.trial(estimator=agent.evaluate, num=48, depth=0, storage="local", seed=4)
+    r2 = rl.QAgent.trial(estimator=agent.evaluate, num=48, depth=2, width=3, since_empty=8, storage="local", seed=4)
+    out = capsys.readouterr().out
+    assert len(r2) == 48 and "average score of 48 runs" in out
+    assert np.mean([g.score for g in r2]) > np.mean([g.score for g in r0])
+    best = r2[0]
+    assert len(best.moves) == best.odometer == len(best.tiles)
+    chain = best.replay(verbose=False)
+    assert np.array_equal(chain[best.odometer][0], best.row) and chain[best.odometer][1] == best.score
+    game = gl.Game()
+    game.trial_run(agent.evaluate, depth=2, width=2, since_empty=8, step_limit=60)
+    assert game.odometer == 60 or game.game_over(game.row)
+    assert len(game.moves) == game.odometer

@@ -470,6 +470,45 @@ def test_finished_game_log_and_delta_apply(eng, orc, fx):
     assert torch.equal(w1[::3], torch.full_like(w1[::3], 0.5)) and not w1[1::3].any().item() and not d1.any().item()
 
 
+@pytest.mark.parametrize("n", [4, 6])
+def test_look_forward_and_expectimax_play_vs_oracle(eng, orc, fx, n):
+    """Game.look_forward / trial_run with look-ahead (game_logic.py:150-183, 214-243): device values and whole games
+    == the float32 oracle, whose recursion is pinned to the reference by tests/golden/lookforward.npz."""
+    ctx, engine, cabi = eng
+    w, wd = w_dev(ctx, fx, n, 12)
+    rng = np.random.default_rng(5)
+    # crowded afterstates: 0-6 empty cells, exponents 1..9
+    rows = rng.integers(1, 10, size=(300, 16)).astype(np.int32)
+    rows[rng.random((300, 16)) < rng.random((300, 1)) * 0.4] = 0
+    rows[np.arange(300), rng.integers(0, 16, size=300)] = 0             # an afterstate always has an empty cell
+    boards = orc.pack_np(rows)
+    ids = rng.integers(0, 1 << 40, size=300).astype(np.uint64)
+    mv = rng.integers(0, 5000, size=300).astype(np.uint32)
+    rd = rng.integers(0, 4, size=300).astype(np.int32)
+    for depth, width, since_empty in ((0, 1, 6), (1, 1, 6), (1, 4, 16), (2, 2, 6), (2, 4, 8), (3, 3, 7), (4, 2, 5)):
+        ref = orc.look_forward(n, w, rows, None, depth, width, since_empty, seed=21, ids=ids, move_no=mv, root_dir=rd)
+        got = ctx.look_forward(n, wd, ctx.to_device(boards), ctx.to_device(ids), ctx.to_device(mv),
+                               ctx.to_device(rd.astype(np.uint8)), depth, width, since_empty, seed=21).cpu().numpy()
+        assert np.array_equal(got, ref), (depth, width, since_empty, np.abs(got - ref).max())
+    num = 24
+    for depth, width, since_empty in ((1, 2, 8), (2, 2, 6), (3, 4, 5)):
+        ref = orc.play_expectimax(n, w, 31, 100, num, depth, width, since_empty, threads=8)
+        games = engine.GameBatch(num, seed=31, ctx=ctx).init(first_id=100)
+        tdir, _, tsp = engine.expectimax_play(ctx, n, wd, games, depth, width, since_empty, chunk=50, trace_len=4096)
+        h, c = games.to_host(), games.read_counters()
+        assert np.array_equal(h["board"], ref["boards"]) and np.array_equal(h["score"].astype(np.int64), ref["scores"])
+        assert np.array_equal(h["moves"].astype(np.int32), ref["moves"])
+        assert c["moves"] == ref["total_moves"] and c["finished"] == num and c["score_sum"] == ref["scores"].sum()
+        td = tdir.cpu().numpy()
+        assert all((td[j, :h["moves"][j]] >= 0).all() and (td[j, h["moves"][j]:] == -2).all() for j in range(num))
+    # depth 0 == greedy play
+    g0 = engine.GameBatch(num, seed=31, ctx=ctx).init(first_id=100)
+    engine.expectimax_play(ctx, n, wd, g0, 0)
+    g1 = engine.GameBatch(num, seed=31, ctx=ctx).init(first_id=100)
+    engine.greedy_play(ctx, n, wd, g1)
+    assert np.array_equal(g0.to_host()["board"], g1.to_host()["board"])
+
+
 def test_argument_errors(eng):
     ctx, engine, cabi = eng
     L = ctx.lib

@@ -269,3 +269,17 @@ def test_play_philox_threads_agree(orc, fx):
     assert np.array_equal(a["scores"], b["scores"]) and np.array_equal(a["boards"], b["boards"])
     assert np.array_equal(a["scores"], np.concatenate([c1["scores"], c2["scores"]]))
     assert a["total_moves"] == a["moves"].sum() > 24 * 20
+
+
+def test_look_forward_replays_reference(orc, fx):
+    """Game.look_forward (game_logic.py:214-243): the oracle, fed the reference's logged random.sample /
+    random.randrange results in call order, reproduces the reference's values (float64, 141 calls, depth 1-4)."""
+    g = load_golden("lookforward.npz")
+    n = int(g["n"])
+    w = fx.flat(fx.init_weights32(n, int(g["w_seed"]))).astype(np.float64)
+    w[g["w_idx"]] = g["w_val"]
+    for q in range(len(g["rows"])):
+        score, depth, width, since_empty = (int(x) for x in g["meta"][q])
+        log = (g["pos"][g["pos_off"][q]:g["pos_off"][q + 1]], g["tile"][g["tile_off"][q]:g["tile_off"][q + 1]])
+        v = orc.look_forward(n, w, g["rows"][q:q + 1], [score], depth, width, since_empty, log=log)[0]
+        assert abs(v - g["values"][q]) <= 1e-9 * max(1.0, abs(g["values"][q])), (q, v, g["values"][q])
