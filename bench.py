@@ -45,7 +45,7 @@ def parse():
     p.add_argument("--stepwise", action="store_true", help="3 launches per lock-step instead of the persistent kernel")
     p.add_argument("--rule", default="mean", choices=["mean", "sum"])
     p.add_argument("--alpha", type=float, default=0.25)
-    p.add_argument("--sync-every", type=int, default=64, help="lock-steps between weight-delta allreduces (N>1)")
+    p.add_argument("--sync-every", type=int, default=128, help="lock-steps between weight-delta allreduces (N>1)")
     p.add_argument("--boards", type=int, default=1 << 24, help="boards per GPU (sweep)")
     p.add_argument("--no-extras", action="store_true")
     p.add_argument("--chunk", type=int, default=4096, help="moves per greedy launch")
