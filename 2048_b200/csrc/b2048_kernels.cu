@@ -141,18 +141,6 @@ __global__ void spawn_replay_kernel(uint64_t *__restrict__ boards, int64_t m, co
 }
 
 // config-5 sweep: persistent CTAs, row LUT (u16) + merge-code LUT (u8) staged in 192 KB of shared memory
-struct LutShared {
-    const uint16_t *row;
-    const uint8_t *code;
-    __device__ __forceinline__ uint32_t operator()(uint32_t line) const
-    {
-        uint32_t r = row[line], c = code[line];
-        uint32_t ovf = ((c & 15u) == 15u) | ((c >> 4) == 15u);
-        uint32_t ch = (r != line) | ovf;
-        return r | (c << 16) | (ch << 24) | (ovf << 25);
-    }
-};
-
 constexpr int SWEEP_THREADS = 1024;
 constexpr size_t SWEEP_SMEM = 65536 * 2 + 65536;
 
