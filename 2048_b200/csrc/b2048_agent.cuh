@@ -1567,6 +1567,10 @@ int launch_persist(int grid, cudaStream_t st, void **args)
     if (occ < 1 || grid > occ * sm_count()) return B2048_ENOTSUP;       // all CTAs must be co-resident
     e = cudaLaunchCooperativeKernel(reinterpret_cast<void *>(kern), dim3(unsigned(grid)), dim3(PERSIST_THREADS), args,
                                     size_t(smem), st);
+    if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorNotSupported || e == cudaErrorLaunchOutOfResources) {
+        cudaGetLastError();                                             // not sticky: the caller takes the stepwise path
+        return B2048_ENOTSUP;
+    }
     return e == cudaSuccess ? 0 : int(e);
 }
 
