@@ -38,7 +38,8 @@ def parse():
     p.add_argument("--depth", type=int, default=3, help="expectimax: look-ahead depth (the reference's best: 3)")
     p.add_argument("--width", type=int, default=4, help="expectimax: sampled tiles per node")
     p.add_argument("--since-empty", type=int, default=6, help="expectimax: look ahead only below this many empty cells")
-    p.add_argument("--n", type=int, default=4)
+    p.add_argument("--n", "--tuple", dest="n", type=int, default=4,
+                   help="tuple size 2..6 (use --tuple under torchrun, whose own parser finds --n ambiguous)")
     p.add_argument("--games", type=int, default=4096, help="game slots per GPU")
     p.add_argument("--lock-steps", type=int, default=2048, help="lock-steps per bench step (td)")
     p.add_argument("--mode", default="atomic", choices=["atomic", "deterministic"])
@@ -666,7 +667,7 @@ def run_sweep(args):
 
 def main():
     args = parse()
-    if args.workload == "greedy" and args.n == 4 and "--n" not in sys.argv:
+    if args.workload == "greedy" and args.n == 4 and "--n" not in sys.argv and "--tuple" not in sys.argv:
         args.n = 6
     if args.workload == "greedy" and "--games" not in sys.argv:
         args.games = 131072
