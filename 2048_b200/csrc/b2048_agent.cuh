@@ -1370,23 +1370,6 @@ td_persist_kernel(PersistBuffers pb, PersistCtrl *ctrl, const uint32_t *__restri
         grid_wait(&ctrl->bar, bar_target);
         if (tl) tl[4] = clock64();
         if (!DIRECT) {
-            auto apply_key = [&](uint32_t k) {
-                float u;
-                if (EXACT) {
-                    const long long qs = (long long)__ldcg(accq + k);
-                    const uint32_t cv = __ldcg(pb.cnt + k);
-                    u = update_value<true, MEAN>(qs, 0.0f, float(cv));
-                    __stcg(accq + k, 0ULL);
-                    __stcg(pb.cnt + k, 0u);
-                } else {
-                    const float2 v = __ldcg(acc2 + k);
-                    u = update_value<false, MEAN>(0, v.x, v.y);
-                    __stcg(acc2 + k, make_float2(0.0f, 0.0f));
-                }
-                add_weight(pb.w, pb.delta, k, u);
-            };
-            // this thread's entry of the dense hot table: its load goes out with the accumulator loads below (one L2
-            // round trip for the whole apply phase)
             float2 hv = make_float2(0.0f, 0.0f);
             unsigned long long hqv = 0;
             uint32_t hcv = 0;
@@ -1426,8 +1409,47 @@ td_persist_kernel(PersistBuffers pb, PersistCtrl *ctrl, const uint32_t *__restri
                     }
                 }
             } else {
+                // generic layout: the CTA's key list, 4 keys per thread and pass with every load of a pass in flight
+                // together (keys, then accumulators + weights, then the arithmetic and the stores)
                 const uint32_t mine = s_cursor;
-                for (uint32_t q = threadIdx.x; q < mine; q += blockDim.x) apply_key(__ldcg(list + q));
+                constexpr int AB = 4;
+                for (uint32_t q0 = threadIdx.x; q0 < mine; q0 += AB * blockDim.x) {
+                    uint32_t kk[AB];
+                    bool on[AB];
+#pragma unroll
+                    for (int a = 0; a < AB; a++) {
+                        const uint32_t q = q0 + a * blockDim.x;
+                        on[a] = q < mine;
+                        kk[a] = on[a] ? __ldcg(list + q) : 0u;
+                    }
+                    float2 av[AB];
+                    long long aq[AB];
+                    uint32_t ac[AB];
+                    float wv2[AB], dv2[AB];
+#pragma unroll
+                    for (int a = 0; a < AB; a++)
+                        if (on[a]) {
+                            if (EXACT) { aq[a] = (long long)__ldcg(accq + kk[a]); ac[a] = __ldcg(pb.cnt + kk[a]); }
+                            else av[a] = __ldcg(acc2 + kk[a]);
+                            wv2[a] = __ldcg(pb.w + kk[a]);
+                            if (pb.delta) dv2[a] = __ldcg(pb.delta + kk[a]);
+                        }
+#pragma unroll
+                    for (int a = 0; a < AB; a++)
+                        if (on[a]) {
+                            float u;
+                            if (EXACT) {
+                                u = update_value<true, MEAN>(aq[a], 0.0f, float(ac[a]));
+                                __stcg(accq + kk[a], 0ULL);
+                                __stcg(pb.cnt + kk[a], 0u);
+                            } else {
+                                u = update_value<false, MEAN>(0, av[a].x, av[a].y);
+                                __stcg(acc2 + kk[a], make_float2(0.0f, 0.0f));
+                            }
+                            __stcg(pb.w + kk[a], __fadd_rn(wv2[a], u));
+                            if (pb.delta) __stcg(pb.delta + kk[a], __fadd_rn(dv2[a], u));
+                        }
+                }
             }
             if (hot_on && (EXACT ? hcv != 0u : hv.y != 0.0f)) {
                 const float u = EXACT ? update_value<true, MEAN>((long long)hqv, 0.0f, float(hcv))
