@@ -688,8 +688,11 @@ look_forward_kernel(const float *__restrict__ w, const uint32_t *__restrict__ lu
 
 // Game.trial_run with look-ahead (game_logic.py:150-183): one warp per game slot, the two half-warps score root
 // directions (0, 1) then (2, 3); strict '>' scanning d = 0..3, commit, Philox spawn.  Whole games per launch.
-template <int N>
-__global__ void __launch_bounds__(128)
+// MINB: resident CTAs per SM the register allocation must allow.  Few games (a warp each) run fastest with all the
+// registers the tree walk wants (166, MINB = 1: 2.0 M moves/s at 1,024 games vs 1.4 M capped); many games want the
+// occupancy (MINB = 6, <= 80 registers: 3.7 M moves/s at 8,192 games vs 2.5 M uncapped).
+template <int N, int MINB>
+__global__ void __launch_bounds__(128, MINB)
 expectimax_play_kernel(const float *__restrict__ w, const uint32_t *__restrict__ lut, b2048_games_t g, int max_steps,
                        int limit_tile, int step_limit, int depth, int width, int since_empty,
                        int8_t *__restrict__ trace_dir, uint16_t *__restrict__ trace_spawn, int64_t trace_len)
@@ -1697,9 +1700,13 @@ int expectimax_play_impl(const float *w, const uint32_t *lut, const b2048_games_
                          int step_limit, int depth, int width, int since_empty, int8_t *trace_dir, uint16_t *trace_spawn,
                          int64_t trace_len, cudaStream_t st)
 {
-    expectimax_play_kernel<N><<<unsigned(cdiv(g->B * 32, 128)), 128, 0, st>>>(w, lut, *g, max_steps, limit_tile, step_limit,
-                                                                             depth, width, since_empty, trace_dir,
-                                                                             trace_spawn, trace_len);
+    const unsigned grid = unsigned(cdiv(g->B * 32, 128));
+    if (g->B <= 2048)
+        expectimax_play_kernel<N, 1><<<grid, 128, 0, st>>>(w, lut, *g, max_steps, limit_tile, step_limit, depth, width,
+                                                          since_empty, trace_dir, trace_spawn, trace_len);
+    else
+        expectimax_play_kernel<N, 6><<<grid, 128, 0, st>>>(w, lut, *g, max_steps, limit_tile, step_limit, depth, width,
+                                                          since_empty, trace_dir, trace_spawn, trace_len);
     return launch_status();
 }
 
