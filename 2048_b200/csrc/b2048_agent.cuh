@@ -449,26 +449,54 @@ __device__ __forceinline__ void best_move(const float *__restrict__ w, const Lut
 #ifndef B2048_GREEDY_MINBLOCKS
 #define B2048_GREEDY_MINBLOCKS 6
 #endif
+// Game.trial_run at depth 0 (game_logic.py:170-183).  4 lanes per game (lane d = direction d).  The grid is
+// persistent and the 4-lane groups take game slots from a queue (g.counters[B2048_CTR_QUEUE]): games end after
+// very different numbers of moves, and with a fixed slot per group a warp would idle until the longest of its 8
+// games is over.  A slot is played until it is DONE or has made max_steps moves in this launch, then written back.
 template <int N>
 __global__ void __launch_bounds__(128, B2048_GREEDY_MINBLOCKS)
 greedy_play_kernel(const float *__restrict__ w, const uint32_t *__restrict__ lut, b2048_games_t g, int max_steps,
                    int limit_tile, int step_limit, b2048_replay_t rp, int has_replay, int8_t *__restrict__ trace_dir,
                    float *__restrict__ trace_value, uint16_t *__restrict__ trace_spawn, int64_t trace_len)
 {
-    const int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
-    const int64_t slot = t >> 2;
-    const int d = int(t & 3);
-    const bool in = slot < g.B;
+    const int lane = threadIdx.x & 31, d = lane & 3;
+    const unsigned gmask = 0xFu << (lane & ~3);
+    unsigned long long *queue = reinterpret_cast<unsigned long long *>(g.counters + B2048_CTR_QUEUE);
     LutGlobal L{lut};
-    uint64_t board = in ? g.board[slot] : 0;
-    uint32_t score = in ? g.score[slot] : 0;
-    uint32_t odo = in ? g.moves[slot] : 0;
-    uint32_t flags = in ? g.flags[slot] : B2048_F_DONE;
-    const uint64_t id = in ? g.game_id[slot] : 0;
-    bool run = in && !(flags & B2048_F_DONE);
-    uint32_t c_moves = 0, c_evals = 0, c_fin = 0, c_score = 0, c_msum = 0, c_ovf = 0;
-    for (int step = 0; step < max_steps; step++) {
-        if (!__any_sync(FULL, run)) break;
+    int64_t slot = -1;
+    uint64_t board = 0, id = 0;
+    uint32_t score = 0, odo = 0, flags = B2048_F_DONE;
+    bool in = false, run = false, more = true;
+    int steps_done = 0;
+    uint32_t c_moves = 0, c_evals = 0, c_fin = 0, c_score = 0, c_msum = 0, c_ovf = 0, c_active = 0;
+    while (true) {
+        // a group whose game is over (or paused, or out of moves for this launch) writes it back and takes the next slot
+        while (more && !(run && steps_done < max_steps)) {
+            if (in && d == 0) {
+                g.board[slot] = board;
+                g.score[slot] = score;
+                g.moves[slot] = odo;
+                g.flags[slot] = uint8_t(flags);
+                if (!(flags & B2048_F_DONE)) c_active++;
+            }
+            unsigned long long nx = 0;
+            if (d == 0) nx = atomicAdd(queue, 1ULL);
+            nx = (unsigned long long)__shfl_sync(gmask, (long long)nx, lane & ~3);
+            slot = int64_t(nx);
+            in = slot < g.B;
+            more = in;
+            board = in ? g.board[slot] : 0;
+            score = in ? g.score[slot] : 0;
+            odo = in ? g.moves[slot] : 0;
+            flags = in ? g.flags[slot] : B2048_F_DONE;
+            id = in ? g.game_id[slot] : 0;
+            run = in && !(flags & B2048_F_DONE);
+            steps_done = 0;
+            if (in && !run) in = false;                             // already finished: nothing to write back
+        }
+        const bool go = run && steps_done < max_steps;
+        if (!__any_sync(FULL, go)) break;                           // every group has drained the queue
+        run = go;
         if (run) {
             bool stop = game_over(board) || (limit_tile && max_tile(board) >= limit_tile) || int(odo) >= step_limit;
             if (stop) {
@@ -481,8 +509,9 @@ greedy_play_kernel(const float *__restrict__ w, const uint32_t *__restrict__ lut
                 }
             }
         }
+        bool paused = false;
         if (run && has_replay) {                                    // recorded spawns exhausted -> pause
-            if (int64_t(odo) >= rp.len || __ldg(rp.tile + slot * rp.len + odo) == 0) run = false;
+            if (int64_t(odo) >= rp.len || __ldg(rp.tile + slot * rp.len + odo) == 0) { run = false; paused = true; }
         }
         uint64_t ba;
         uint32_t bg, bf, nv;
@@ -520,14 +549,17 @@ greedy_play_kernel(const float *__restrict__ w, const uint32_t *__restrict__ lut
                     sp = spawn_apply(board, r.x, r.y);
                 }
                 if (d == 0 && trace_spawn && int64_t(odo) <= trace_len) trace_spawn[slot * trace_len + odo - 1] = uint16_t(sp);
+                steps_done++;
             }
         }
+        (void)paused;
     }
-    if (in && d == 0) {
+    if (in && d == 0) {                                             // the game the group still holds
         g.board[slot] = board;
         g.score[slot] = score;
         g.moves[slot] = odo;
         g.flags[slot] = uint8_t(flags);
+        if (!(flags & B2048_F_DONE)) c_active++;
     }
     warp_add_counter(g.counters + B2048_CTR_MOVES, c_moves);
     warp_add_counter(g.counters + B2048_CTR_EVALS, c_evals);
@@ -535,7 +567,7 @@ greedy_play_kernel(const float *__restrict__ w, const uint32_t *__restrict__ lut
     warp_add_counter(g.counters + B2048_CTR_SCORE_SUM, c_score);
     warp_add_counter(g.counters + B2048_CTR_MOVES_SUM, c_msum);
     warp_add_counter(g.counters + B2048_CTR_OVERFLOW, c_ovf);
-    warp_add_counter(g.counters + B2048_CTR_ACTIVE, (in && d == 0 && !(flags & B2048_F_DONE)) ? 1u : 0u);
+    warp_add_counter(g.counters + B2048_CTR_ACTIVE, c_active);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1679,7 +1711,11 @@ int greedy_play_impl(const float *w, const uint32_t *lut, const b2048_games_t *g
                      uint16_t *trace_spawn, int64_t trace_len, cudaStream_t st)
 {
     b2048_replay_t rp = replay ? *replay : b2048_replay_t{nullptr, nullptr, 0};
-    unsigned grid = unsigned(cdiv(g->B * 4, 128));
+    int occ = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, greedy_play_kernel<N>, 128, 0);
+    if (e != cudaSuccess) return int(e);
+    const int64_t want = cdiv(g->B * 4, 128), cap = int64_t(sm_count()) * (occ > 0 ? occ : 1);
+    const unsigned grid = unsigned(want < cap ? want : cap);           // persistent: groups pull slots from the queue
     greedy_play_kernel<N><<<grid, 128, 0, st>>>(w, lut, *g, max_steps, limit_tile, step_limit, rp, replay ? 1 : 0, trace_dir,
                                                trace_value, trace_spawn, trace_len);
     return launch_status();

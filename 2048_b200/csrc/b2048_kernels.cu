@@ -446,7 +446,12 @@ int b2048_greedy_play(int n, const float *weights, const uint32_t *lut, const b2
     if (replay && (!replay->tile || !replay->pos || replay->len < 0)) return B2048_EINVAL;
     if (g->B == 0) return 0;
     cudaError_t e = cudaMemsetAsync(g->counters + B2048_CTR_ACTIVE, 0, sizeof(uint64_t), S(stream));
+    if (e == cudaSuccess) e = cudaMemsetAsync(g->counters + B2048_CTR_QUEUE, 0, sizeof(uint64_t), S(stream));
     if (e != cudaSuccess) return int(e);
+    if (max_steps == 0) {                                                    // nothing to play: every open slot stays active
+        return agent_ops(n)->greedy_play(weights, lut, g, 0, limit_tile, step_limit, replay, trace_dir, trace_value,
+                                         trace_spawn, trace_len, S(stream));
+    }
     return agent_ops(n)->greedy_play(weights, lut, g, max_steps, limit_tile, step_limit, replay, trace_dir, trace_value,
                                      trace_spawn, trace_len, S(stream));
 }

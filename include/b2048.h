@@ -170,6 +170,7 @@ enum {
     B2048_CTR_OVERFLOW = 6,
     B2048_CTR_ACTIVE = 7,   /* greedy_play: slots still playing after the call (overwritten) */
     B2048_CTR_LOG = 8,      /* finished-game records appended to fin_log (host may reset to 0) */
+    B2048_CTR_QUEUE = 9,    /* greedy_play: next slot to hand out (work queue of the running launch, overwritten) */
     B2048_CTR_COUNT = 16
 };
 
