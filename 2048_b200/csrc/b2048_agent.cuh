@@ -509,9 +509,8 @@ greedy_play_kernel(const float *__restrict__ w, const uint32_t *__restrict__ lut
                 }
             }
         }
-        bool paused = false;
-        if (run && has_replay) {                                    // recorded spawns exhausted -> pause
-            if (int64_t(odo) >= rp.len || __ldg(rp.tile + slot * rp.len + odo) == 0) { run = false; paused = true; }
+        if (run && has_replay) {                                    // recorded spawns exhausted -> pause (stays not DONE)
+            if (int64_t(odo) >= rp.len || __ldg(rp.tile + slot * rp.len + odo) == 0) run = false;
         }
         uint64_t ba;
         uint32_t bg, bf, nv;
@@ -552,7 +551,6 @@ greedy_play_kernel(const float *__restrict__ w, const uint32_t *__restrict__ lut
                 steps_done++;
             }
         }
-        (void)paused;
     }
     if (in && d == 0) {                                             // the game the group still holds
         g.board[slot] = board;
