@@ -521,3 +521,22 @@ def test_argument_errors(eng):
                              engine.dptr(ctx.zeros(4, torch.float32)), 4, 3, None, 0, None) == -3     # EWORK
     assert L.b2048_td_update(4, engine.dptr(b), None, engine.dptr(b), engine.dptr(b), 4, 4, None, 0, None) == -1  # SORTED needs DETERMINISTIC
     assert b"workspace" in L.b2048_strerror(-3)
+    # b2048_td_run: launch plan and argument checks
+    assert L.b2048_td_run_launches(4, 4096, cabi.UPD_ATOMIC | cabi.UPD_MEAN, 100) == 1            # persistent kernel
+    assert L.b2048_td_run_launches(4, 4096, cabi.UPD_ATOMIC | cabi.UPD_MEAN | cabi.RUN_STEPWISE, 100) == 300
+    assert L.b2048_td_run_launches(4, 4096, cabi.UPD_ATOMIC | cabi.UPD_SUM | cabi.RUN_STEPWISE, 100) == 200
+    assert L.b2048_td_run_launches(4, 0, 0, 100) == 0 and L.b2048_td_run_launches(7, 16, 0, 1) == -1
+    games = engine.GameBatch(8, seed=1, ctx=ctx).init()
+    w = ctx.zeros(cabi.num_weights(4), torch.float32)
+    tr = engine.TDTrainer(ctx, 4, w, games, 0.25, cabi.UPD_ATOMIC | cabi.UPD_MEAN)
+    assert L.b2048_td_run(4, engine.dptr(w), None, engine.dptr(ctx.lut), C.byref(games.c), C.c_float(0.25), 2, 5,
+                          engine.dptr(tr.upd_board), engine.dptr(tr.upd_dw), None, 0, None) == -3   # no workspace
+    assert L.b2048_td_run(4, engine.dptr(w), None, engine.dptr(ctx.lut), C.byref(games.c), C.c_float(0.25), 16, 5,
+                          engine.dptr(tr.upd_board), engine.dptr(tr.upd_dw), engine.dptr(tr.work), tr.work.numel(),
+                          None) == -1                                                               # unknown mode bit
+    # look-ahead entry points
+    assert L.b2048_look_forward(4, engine.dptr(w), engine.dptr(ctx.lut), None, None, None, None, 0, 5, 1, 6, 0, None, None) == -1
+    assert L.b2048_look_forward(4, engine.dptr(w), engine.dptr(ctx.lut), None, None, None, None, 0, 2, 5, 6, 0, None, None) == -1
+    assert L.b2048_look_forward(4, engine.dptr(w), engine.dptr(ctx.lut), None, None, None, None, 0, 2, 2, 6, 0, None, None) == 0
+    assert L.b2048_expectimax_play(4, engine.dptr(w), engine.dptr(ctx.lut), C.byref(games.c), 4, 0, 100, 9, 1, 6, None, None, 0,
+                                   None) == -1
