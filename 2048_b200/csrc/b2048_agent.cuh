@@ -148,34 +148,45 @@ td_accum_kernel(float *__restrict__ w, float *__restrict__ delta, void *__restri
 }
 
 // ---- apply pass: one thread per touched key, plain loads/stores --------------------------------
-template <bool EXACT, bool MEAN, bool COHERENT>
+// Every load of a key (count, the R accumulator replicas, the old weight) is issued before the first store: stores to
+// addresses the compiler cannot tell apart from the next loads would otherwise put one L2 round trip per replica on
+// the critical path (8 of them at n <= 5).
+template <bool EXACT, bool MEAN, int R>
 __device__ __forceinline__ void apply_key(float *__restrict__ w, float *__restrict__ delta, void *__restrict__ acc,
-                                          uint32_t *__restrict__ cnt, uint32_t k, int64_t nw, int R)
+                                          uint32_t *__restrict__ cnt, uint32_t k, int64_t nw)
 {
-    const uint32_t c = COHERENT ? __ldcg(cnt + k) : cnt[k];
+    const uint32_t c = cnt[k];
+    const float wk = w[k];
+    const float dk = delta ? delta[k] : 0.0f;
     float u;
     if (EXACT) {
         long long *a = reinterpret_cast<long long *>(acc) + k;
+        long long v[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) v[r] = a[r * nw];
         long long qs = 0;
+#pragma unroll
         for (int r = 0; r < R; r++) {
-            long long v = COHERENT ? __ldcg(a + r * nw) : a[r * nw];
-            if (v) { qs += v; a[r * nw] = 0; }
+            qs += v[r];
+            if (v[r]) a[r * nw] = 0;
         }
         double x = double(qs) / FIX_SCALE;
         if (MEAN) x = x / double(c);
         u = __double2float_rn(x);
     } else {
         float *a = reinterpret_cast<float *>(acc) + k;
+        float v[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) v[r] = a[r * nw];
         float fs = 0.0f;
-        for (int r = 0; r < R; r++) {
-            float v = COHERENT ? __ldcg(a + r * nw) : a[r * nw];
-            if (v != 0.0f) { fs += v; a[r * nw] = 0.0f; }
-        }
+#pragma unroll
+        for (int r = 0; r < R; r++)
+            if (v[r] != 0.0f) { fs += v[r]; a[r * nw] = 0.0f; }
         u = MEAN ? __fdiv_rn(fs, float(c)) : fs;
     }
     cnt[k] = 0;
-    w[k] = __fadd_rn(COHERENT ? __ldcg(w + k) : w[k], u);
-    if (delta) delta[k] = __fadd_rn(COHERENT ? __ldcg(delta + k) : delta[k], u);
+    w[k] = __fadd_rn(wk, u);
+    if (delta) delta[k] = __fadd_rn(dk, u);
 }
 
 template <bool EXACT, bool MEAN>
@@ -183,10 +194,11 @@ __global__ void __launch_bounds__(256)
 td_apply_kernel(float *__restrict__ w, float *__restrict__ delta, void *__restrict__ acc, uint32_t *__restrict__ cnt,
                 const uint32_t *__restrict__ touched, UpdCtrl *__restrict__ ctrl, int64_t nw)
 {
-    const int R = acc_replicas(nw);
     const uint32_t count = *reinterpret_cast<volatile uint32_t *>(&ctrl->count);
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < count; t += gridDim.x * blockDim.x)
-        apply_key<EXACT, MEAN, false>(w, delta, acc, cnt, touched[t], nw, R);
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < count; t += gridDim.x * blockDim.x) {
+        if (acc_replicas(nw) == 8) apply_key<EXACT, MEAN, 8>(w, delta, acc, cnt, touched[t], nw);
+        else apply_key<EXACT, MEAN, 2>(w, delta, acc, cnt, touched[t], nw);
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
