@@ -71,60 +71,16 @@ __device__ __forceinline__ void accumulate_key(bool exact, void *__restrict__ ac
     if (old == 0) touched[atomicAdd(&ctrl->count, 1u)] = uint32_t(k);
 }
 
-// The contributions of one (entry, image) lane for the tables i with i % CH == chunk (CH = 1: all tables).
-// Must be called by all 32 lanes of a warp with a warp-uniform `chunk`; lanes 8k..8k+7 hold the 8 images of
-// one entry.
-template <int N, bool EXACT, bool MEAN, bool DIRECT, int CH>
-__device__ __forceinline__ void accum_features(float *__restrict__ w, float *__restrict__ delta, void *__restrict__ acc,
-                                               uint32_t *__restrict__ cnt, uint32_t *__restrict__ touched,
-                                               uint32_t *__restrict__ count, uint64_t b, float d, bool live, int s,
-                                               int lane, int chunk, int64_t replica_off)
+// One thread per (entry, table): the 8 D4 image keys of the table, a duplicate test among them in registers (an
+// entry counts once per key in G), one atomic per key into the CTA's accumulator replica, and the keys whose count
+// went 0 -> >0 appended to the touched list (one warp scan + one global atomic per warp).  No warp-level key
+// matching: __match_any_sync costs ~12 cycles per distinct value (profiles/r01b_microbench_warpops.txt).
+template <int N>
+__device__ __forceinline__ uint32_t table_offset_rt0(int i)
 {
-    const uint64_t y = (N == 6) ? clamp13(b) : 0;
-    const long long q = (EXACT && live) ? quantize(d) : 0;
-    for_each_feature<N>([&](auto I) {
-        constexpr int i = decltype(I)::value;
-        if (CH > 1 && (i % CH) != chunk) return;
-        const uint32_t f = feat_index<N, i>(b, y);
-        const uint32_t k = uint32_t(table_offset(N, i)) + f;
-        uint32_t first = 1;
-        if (MEAN) {                                   // is a lower image of the same entry on the same key?
-#pragma unroll
-            for (int o = 1; o < 8; o++) {
-                uint32_t fo = __shfl_xor_sync(FULL, f, o);
-                if (fo == f && (s ^ o) < s) first = 0;
-            }
-        }
-        const uint32_t peers = __match_any_sync(FULL, live ? k : 0xFFFFFFFFu - uint32_t(lane));
-        float fsum = d;
-        long long qsum = q;
-        uint32_t nf = first;
-        if (peers & (peers - 1)) {                    // more than one lane on this key: merge (group-uniform branch)
-            fsum = 0.0f; qsum = 0; nf = 0;
-            for (uint32_t mm = peers; mm; mm &= mm - 1) {
-                const int src = __ffs(mm) - 1;
-                if (EXACT) {
-                    qsum += __shfl_sync(peers, q, src);
-                } else {
-                    fsum += __shfl_sync(peers, d, src);
-                }
-                if (MEAN) nf += __shfl_sync(peers, first, src);
-            }
-            if (!MEAN) nf = 1;
-        }
-        if (live && lane == __ffs(peers) - 1) {
-            if (DIRECT) {
-                atomicAdd(w + k, fsum);
-                if (delta) atomicAdd(delta + k, fsum);
-            } else {
-                if (EXACT)
-                    atomicAdd(reinterpret_cast<unsigned long long *>(acc) + replica_off + k, (unsigned long long)qsum);
-                else
-                    atomicAdd(reinterpret_cast<float *>(acc) + replica_off + k, fsum);
-                if (atomicAdd(cnt + k, nf) == 0) touched[atomicAdd(count, 1u)] = k;
-            }
-        }
-    });
+    if (N <= 4) return uint32_t(i) * uint32_t(table_size(N, 0));
+    return i <= 17 ? uint32_t(i) * 65536u : i <= 21 ? 17u * 65536u + uint32_t(i - 17) * 1048576u
+                                                    : 17u * 65536u + 4u * 1048576u + uint32_t(i - 21) * 7529536u;
 }
 
 template <int N, bool EXACT, bool MEAN, bool DIRECT>
@@ -133,18 +89,75 @@ td_accum_kernel(float *__restrict__ w, float *__restrict__ delta, void *__restri
                 uint32_t *__restrict__ touched, UpdCtrl *__restrict__ ctrl, const uint64_t *__restrict__ boards,
                 const float *__restrict__ dw, int64_t m)
 {
+    constexpr int F = num_feat(N);
+    constexpr int MAXC = N;
     const int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
-    const int64_t j = t >> 3;
-    const int s = int(t & 7), lane = threadIdx.x & 31;
+    const int64_t j = t / F;
+    const int tab = int(t % F), lane = threadIdx.x & 31;
     const bool on = j < m;
     const float d = on ? __ldg(dw + j) : NAN;
     const bool live = on && (EXACT ? isfinite(d) : !isnan(d));
     if (!__any_sync(FULL, live)) return;
-    const uint64_t b = d4_image(on ? __ldg(boards + j) : 0, s);
+    const FeatSpec spec = feat_spec(N, tab);
+    const bool base14 = spec.base == 14;
+    const uint32_t key_off = table_offset_rt0<N>(tab);
+    uint64_t img[8];
+    const uint64_t b0 = on ? __ldg(boards + j) : 0;
+    img[0] = base14 ? clamp13(b0) : b0;
+    img[1] = flip_h(img[0]);
+    img[2] = flip_v(img[0]);
+    img[3] = flip_v(img[1]);
+#pragma unroll
+    for (int s = 0; s < 4; s++) img[4 + s] = transpose(img[s]);
     constexpr int64_t NW = table_offset(N, num_feat(N));
     const int64_t replica_off = int64_t(blockIdx.x % acc_replicas(NW)) * NW;
-    accum_features<N, EXACT, MEAN, DIRECT, 1>(w, delta, acc, cnt, touched, ctrl ? &ctrl->count : nullptr, b, d, live, s,
-                                              lane, 0, replica_off);
+    const long long qd = (EXACT && live) ? quantize(d) : 0;
+    uint32_t idx[8], old[8];
+#pragma unroll
+    for (int s = 0; s < 8; s++) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int k = 0; k < MAXC; k++)
+            if (k < spec.ncell) {
+                const uint32_t cell = uint32_t(img[s] >> (4 * (15 - spec.cell[k]))) & 15u;
+                v = base14 ? v * 14u + cell : (v << 4) | cell;
+            }
+        idx[s] = v;
+        bool ld = true;                                   // no lower image of this entry has the same key
+#pragma unroll
+        for (int o = 0; o < s; o++) ld &= idx[o] != v;
+        old[s] = 1u;
+        if (!live) continue;
+        const uint32_t k = key_off + v;
+        if (DIRECT) {
+            atomicAdd(w + k, d);
+            if (delta) atomicAdd(delta + k, d);
+        } else {
+            if (EXACT) atomicAdd(reinterpret_cast<unsigned long long *>(acc) + replica_off + k, (unsigned long long)qd);
+            else atomicAdd(reinterpret_cast<float *>(acc) + replica_off + k, d);
+            if (ld) old[s] = atomicAdd(cnt + k, 1u);
+        }
+    }
+    if (DIRECT) return;
+    uint32_t first = 0;
+#pragma unroll
+    for (int s = 0; s < 8; s++) first |= uint32_t(old[s] == 0u) << s;
+    const uint32_t mine = __popc(first);
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t up = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += up;
+    }
+    const uint32_t total = __shfl_sync(FULL, incl, 31);
+    if (total) {                                          // warp-uniform
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&ctrl->count, total);
+        uint32_t pos = __shfl_sync(FULL, base, 0) + incl - mine;
+#pragma unroll
+        for (int s = 0; s < 8; s++)
+            if ((first >> s) & 1u) touched[pos++] = key_off + idx[s];
+    }
 }
 
 // ---- apply pass: one thread per touched key, plain loads/stores --------------------------------
@@ -1566,7 +1579,7 @@ int td_update_impl(float *weights, float *delta, const uint64_t *boards, const f
     if (m == 0) return 0;
     const bool det = mode & B2048_UPD_DETERMINISTIC, mean = mode & B2048_UPD_MEAN, sorted = mode & B2048_UPD_SORTED;
     if (sorted && !det) return B2048_EINVAL;
-    const unsigned grid = unsigned(cdiv(m * 8, 128));
+    const unsigned grid = unsigned(cdiv(m * num_feat(N), 128));       // accumulate: one thread per (entry, table)
     if (!det && !mean) {
         launch_accum<N, false, false, true>(grid, st, weights, delta, nullptr, nullptr, nullptr, nullptr,
                                                           boards, dw, m);
@@ -1586,7 +1599,7 @@ int td_update_impl(float *weights, float *delta, const uint64_t *boards, const f
         uint32_t *ka = reinterpret_cast<uint32_t *>(base + L.keys_a), *kb = reinterpret_cast<uint32_t *>(base + L.keys_b);
         uint32_t *va = reinterpret_cast<uint32_t *>(base + L.vals_a), *vb = reinterpret_cast<uint32_t *>(base + L.vals_b);
         uint32_t *hist = reinterpret_cast<uint32_t *>(base + L.hist);
-        td_keys_kernel<N><<<grid, 128, 0, st>>>(boards, dw, m, ka, va);
+        td_keys_kernel<N><<<unsigned(cdiv(m * 8, 128)), 128, 0, st>>>(boards, dw, m, ka, va);   // thread per (entry, image)
         const int bits = key_bits(N);
         const int passes = (bits + 7) / 8;
         const int per = (bits + passes - 1) / passes;       // digit width, equal for all passes

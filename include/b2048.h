@@ -121,7 +121,8 @@ int b2048_evaluate(int n, const float *weights, const uint64_t *boards, int64_t 
  *   B2048_UPD_MEAN           w[k] += S[k] / G[k], G[k] = number of DISTINCT entries contributing to
  *                            k: the batched rule that stays stable at the reference's alpha when
  *                            many games hit the same key in one lock-step; == SUM at m == 1
- * Within a warp, lanes that hit the same key are merged before the atomic (hot keys such as empty rows).
+ * One thread handles the 8 images of one (entry, table) pair; the accumulators are replicated per CTA group against
+ * same-address atomics on hot keys (empty rows, small tiles).
  * delta (may be NULL) receives the same increments as weights (multi-GPU delta buffer).
  * work: b2048_td_update_workspace(n, m, mode) bytes (b2048_td_update itself ignores it for ATOMIC|SUM; the
  * fused loops below always need it); zero it once before the first call; every call leaves it ready for the
