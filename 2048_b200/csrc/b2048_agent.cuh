@@ -42,14 +42,12 @@ __global__ void evaluate_kernel(const float *__restrict__ w, const uint64_t *__r
 // TD update: 8 D4 images x F tables per (board, dw)
 // ------------------------------------------------------------------------------------------------
 
-// ---- accumulate pass -------------------------------------------------------------------------
-// Thread per (entry j, image s); the 8 images of an entry are 8 adjacent lanes, a warp holds 4 entries.
-// For every table i the warp first merges lanes that hit the same key (__match_any_sync): hot keys
-// (empty rows/squares early in a game) would otherwise serialise thousands of same-address atomics in L2.
-//   DIRECT          atomic + sum rule: the merged contribution goes straight into w (and delta)
+// ---- accumulate pass (stepwise path: b2048_td_update / b2048_td_step) ---------------------------
+// Thread per (entry j, table i): the keys of the 8 D4 images, duplicates among them found in registers.
+//   DIRECT          atomic + sum rule: every contribution goes straight into w (and delta)
 //   otherwise       acc[k] += contribution (float RED, or exact int64 fixed point when EXACT),
-//                   cnt[k] += number of distinct entries (MEAN) or 1; the lane that sees cnt go 0 -> >0
-//                   appends k to the touched list, so the apply pass needs no atomics at all.
+//                   cnt[k] += 1 per entry and key (G of the MEAN rule; a touched marker otherwise); the thread that
+//                   sees cnt go 0 -> >0 appends k to the touched list, so the apply pass needs no atomics at all.
 constexpr double FIX_SCALE = 4294967296.0;      // 2^32: exact-mode contributions are llrint(dw * 2^32)
 
 
