@@ -18,6 +18,10 @@ p.add_argument("--episodes", type=int, default=100000)
 p.add_argument("--batch", type=int, default=4096)
 p.add_argument("--games", type=int, default=1000)
 p.add_argument("--mode", default="atomic")
+p.add_argument("--depth", type=int, default=0)
+p.add_argument("--width", type=int, default=1)
+p.add_argument("--since-empty", type=int, default=6)
+p.add_argument("--look-games", type=int, default=100)
 a = p.parse_args()
 importlib.import_module("2048_b200")
 from game2048 import r_learning as rl
@@ -33,3 +37,8 @@ h = agent.train_history
 print(f"n={a.n} batch={a.batch} mode={a.mode}: {agent.step} episodes in {dt:.1f} s; ma_100 every 10k episodes: "
       f"{[h[i] for i in range(99, len(h), 100)]}; final alpha {agent.alpha}")
 res = rl.QAgent.trial(estimator=agent.evaluate, num=a.games, storage="local", seed=1)
+if a.depth > 0:
+    t0 = time.time()
+    res = rl.QAgent.trial(estimator=agent.evaluate, num=a.look_games, depth=a.depth, width=a.width, since_empty=a.since_empty,
+                          storage="local", seed=2)
+    print(f"look-ahead trial depth={a.depth} width={a.width} since_empty={a.since_empty}: {a.look_games} games in {time.time() - t0:.1f} s")
