@@ -161,3 +161,40 @@ def test_look_ahead_drivers(mods, fx, capsys):
     game.trial_run(agent.evaluate, depth=2, width=2, since_empty=8, step_limit=60)
     assert game.odometer == 60 or game.game_over(game.row)
     assert len(game.moves) == game.odometer
+
+
+def test_thread_mode_hooks(mods, fx, capsys):
+    """the Dash call sites run the path from daemon threads with cooperative stop flags
+    (application.py:427-468, 566-621; game_logic.py:186-200; r_learning.py:285-290, 363-368)."""
+    import time as _time
+    gl, rl = mods
+    from game2048 import start
+    random.seed(2)
+    agent = agent_from(rl, fx, 4, fx.init_weights32(4, 5))
+    # 'Agent Play': thread_trial records history until the pane's id changes
+    start.GAME_PANE["u1"] = {"id": 7}
+    game = gl.Game()
+    game.thread_trial(agent.evaluate, depth=0, width=1, since_empty=6, stopper={"parent": "u1", "n": 7})
+    t0 = _time.time()
+    while len(game.history) < 20 and _time.time() - t0 < 60:
+        _time.sleep(0.01)
+    start.GAME_PANE["u1"]["id"] = 8                                       # another job took the pane: the thread must stop
+    _time.sleep(0.3)
+    n_hist = len(game.history)
+    _time.sleep(0.3)
+    assert n_hist >= 20 and len(game.history) == n_hist
+    row0, score0, dir0 = game.history[0]
+    assert row0.shape == (4, 4) and score0 == 0 and dir0 in (0, 1, 2, 3)
+    # 'Train' from a thread with a stopper: stops at the next chunk boundary once the pane changes hands
+    from threading import Thread
+    start.AGENT_PANE["u1"] = {"id": 3}
+    start.RUNNING["u1"] = 1
+    worker = Thread(target=agent.train_run, kwargs={"num_eps": 10 ** 7, "saving": False, "batch": 64,
+                                                    "stopper": {"parent": "u1", "a": 3}}, daemon=True)
+    worker.start()
+    t0 = _time.time()
+    while agent.step < 50 and _time.time() - t0 < 60:
+        _time.sleep(0.01)
+    start.AGENT_PANE["u1"]["id"] = 4
+    worker.join(timeout=30)
+    assert not worker.is_alive() and 50 <= agent.step < 10 ** 6
