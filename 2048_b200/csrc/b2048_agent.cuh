@@ -721,7 +721,136 @@ __device__ __forceinline__ float lf_top(const float *__restrict__ w, const uint3
     return __fdiv_rn(average, float(num));
 }
 
-// m afterstates, 16 lanes each
+// The same value for depth >= 2 by a whole warp: the two upper levels of the tree are laid out explicitly -- 16
+// level-1 nodes (tile j, direction d) and up to 256 level-2 afterstates (j, d, j2, d2) -- and the 32 lanes share the
+// level-2 afterstates, each walking the subtree below its items depth-first.  With 16 items of very different
+// size only (lf_top) a third of the lanes were active per instruction.  Arena: per-warp shared memory.
+struct LfArena {
+    uint64_t board[16];      // level-1 afterstates
+    uint32_t pos2[16];       // their 4 sampled cells (6-bit shifts)
+    uint32_t meta[16];       // bit 0-1 state (0 invalid, 1 evaluate directly, 2 expand), bits 4-6 num2, 8-11 tile2 ("4" bits),
+                             // 12-15 game over after spawn j2
+    float value1[16];        // direct values
+    float value2[256];       // level-2 values
+};
+
+template <int N>
+__device__ __forceinline__ float lf_top2(const float *__restrict__ w, const uint32_t *__restrict__ lut, uint64_t b, int depth,
+                                         uint32_t path, const LfParams &P, int lane, LfArena &A)
+{
+    const uint64_t z = zero_nibbles(b);
+    const int empty = popc64(z);
+    if (empty >= P.since_empty) {
+        if (P.evals && lane == 0) ++*P.evals;
+        return evaluate<N>(w, b);
+    }
+    const int num = P.width < empty ? P.width : empty;
+    LutGlobal L{lut};
+    // ---- level 1: lanes 0..15 = (j, d)
+    const int j = (lane >> 2) & 3, d = lane & 3;
+    bool over1 = false;
+    if (lane < 16) {
+        const Philox4 wp = spawn_words(P.seed, P.id, P.move_no, 2u | (path << 8));
+        const Philox4 wt = spawn_words(P.seed, P.id, P.move_no, 3u | (path << 8));
+        const uint32_t rp[4] = {wp.x, wp.y, wp.z, wp.w}, rt[4] = {wt.x, wt.y, wt.z, wt.w};
+        uint64_t left_mask = z, nb = b;
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            if (q < num) {
+                const int sh = kth_empty_shift(left_mask, int(umulhi32(rp[q], uint32_t(empty - q))));
+                left_mask &= ~(1ULL << sh);
+                if (q == j) nb = b | (uint64_t(umulhi32(rt[q], 10u) == 0 ? 2u : 1u) << sh);
+            }
+        const bool active = j < num;
+        over1 = active && game_over(nb);
+        uint32_t gain, fl;
+        const uint64_t a1 = move_dir(L, nb, d, gain, fl);
+        uint32_t meta = 0, pos2 = 0;
+        if (active && !over1 && (fl & 3u) == 1u) {
+            const uint64_t z1 = zero_nibbles(a1);
+            const int empty1 = popc64(z1);
+            if (empty1 >= P.since_empty) {                      // depth - 1 >= 1 here
+                meta = 1u;
+                A.value1[lane] = lf_leaf<N>(w, a1, P);
+            } else {
+                const uint32_t path1 = path * 16u + 4u * uint32_t(j) + uint32_t(d);
+                const int num2 = P.width < empty1 ? P.width : empty1;
+                const Philox4 vp = spawn_words(P.seed, P.id, P.move_no, 2u | (path1 << 8));
+                const Philox4 vt = spawn_words(P.seed, P.id, P.move_no, 3u | (path1 << 8));
+                const uint32_t sp[4] = {vp.x, vp.y, vp.z, vp.w}, st[4] = {vt.x, vt.y, vt.z, vt.w};
+                uint64_t lm = z1;
+                meta = 2u | (uint32_t(num2) << 4);
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (q < num2) {
+                        const int sh = kth_empty_shift(lm, int(umulhi32(sp[q], uint32_t(empty1 - q))));
+                        lm &= ~(1ULL << sh);
+                        const uint32_t four = umulhi32(st[q], 10u) == 0 ? 1u : 0u;
+                        pos2 |= uint32_t(sh) << (6 * q);
+                        meta |= four << (8 + q);
+                        if (game_over(a1 | (uint64_t(1u + four) << sh))) meta |= 1u << (12 + q);
+                    }
+            }
+        }
+        A.board[lane] = a1;
+        A.pos2[lane] = pos2;
+        A.meta[lane] = meta;
+    }
+    __syncwarp();
+    // ---- level 2: 256 items (j, d, j2, d2) over the 32 lanes
+#pragma unroll 1
+    for (int it = lane; it < 256; it += 32) {
+        const int l = it >> 4, j2 = (it >> 2) & 3, d2 = it & 3;
+        const uint32_t meta = A.meta[l];
+        float v = -INFINITY;
+        if ((meta & 3u) == 2u && j2 < int((meta >> 4) & 7u) && !((meta >> (12 + j2)) & 1u)) {
+            const int sh = int((A.pos2[l] >> (6 * j2)) & 63u);
+            const uint64_t nb2 = A.board[l] | (uint64_t(1u + ((meta >> (8 + j2)) & 1u)) << sh);
+            uint32_t gain, fl;
+            const uint64_t a2 = move_dir(L, nb2, d2, gain, fl);
+            if ((fl & 3u) == 1u) {
+                const uint32_t path2 = (path * 16u + uint32_t(l)) * 16u + 4u * uint32_t(j2) + uint32_t(d2);
+                v = lf_dispatch<N>(w, lut, a2, depth - 2, path2, P);
+            }
+        }
+        A.value2[it] = v;
+    }
+    __syncwarp();
+    // ---- back up: level 2 -> level 1 (lanes 0..15), level 1 -> root
+    float best = -INFINITY;
+    if (lane < 16) {
+        const uint32_t meta = A.meta[lane];
+        if ((meta & 3u) == 1u) {
+            best = A.value1[lane];
+        } else if ((meta & 3u) == 2u) {
+            const int num2 = int((meta >> 4) & 7u);
+            float avg = 0.0f;
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                if (q < num2) {
+                    float bq = fmaxf(fmaxf(A.value2[lane * 16 + 4 * q], A.value2[lane * 16 + 4 * q + 1]),
+                                     fmaxf(A.value2[lane * 16 + 4 * q + 2], A.value2[lane * 16 + 4 * q + 3]));
+                    if ((meta >> (12 + q)) & 1u) bq = -100.0f;
+                    avg = __fadd_rn(avg, bq > 0.0f ? bq : 0.0f);
+                }
+            best = __fdiv_rn(avg, float(num2));
+        }
+    }
+    best = fmaxf(best, __shfl_xor_sync(FULL, best, 1));
+    best = fmaxf(best, __shfl_xor_sync(FULL, best, 2));
+    if (over1) best = -100.0f;
+    const float c = best > 0.0f ? best : 0.0f;
+    float average = 0.0f;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const float cq = __shfl_sync(FULL, c, 4 * q);
+        if (q < num) average = __fadd_rn(average, cq);
+    }
+    __syncwarp();                                                  // the arena is reused by the next call
+    return __fdiv_rn(average, float(num));
+}
+
+// m afterstates, one warp each (depth <= 1: the two half-warps compute the same value with lf_top)
 template <int N>
 __global__ void __launch_bounds__(128)
 look_forward_kernel(const float *__restrict__ w, const uint32_t *__restrict__ lut, const uint64_t *__restrict__ boards,
@@ -729,14 +858,15 @@ look_forward_kernel(const float *__restrict__ w, const uint32_t *__restrict__ lu
                     const uint8_t *__restrict__ root_dir, int64_t m, int depth, int width, int since_empty, uint64_t seed,
                     float *__restrict__ value)
 {
-    const int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
-    const int64_t q = t >> 4;
-    const int hl = int(t & 15);
-    const unsigned hmask = 0xFFFFu << (threadIdx.x & 16);
-    if (q >= m) return;                                                   // uniform per half-warp
+    __shared__ LfArena arena[4];
+    const int64_t q = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (q >= m) return;                                                   // warp-uniform
     const LfParams P{seed, __ldg(game_id + q), __ldg(move_no + q), width, since_empty, nullptr};
-    const float v = lf_top<N>(w, lut, __ldg(boards + q), depth, 4u + uint32_t(__ldg(root_dir + q) & 3), P, hl, hmask);
-    if (hl == 0) value[q] = v;
+    const uint32_t path = 4u + uint32_t(__ldg(root_dir + q) & 3);
+    const float v = depth >= 2 ? lf_top2<N>(w, lut, __ldg(boards + q), depth, path, P, lane, arena[threadIdx.x >> 5])
+                               : lf_top<N>(w, lut, __ldg(boards + q), depth, path, P, lane & 15, 0xFFFFu << (lane & 16));
+    if (lane == 0) value[q] = v;
 }
 
 // Game.trial_run with look-ahead (game_logic.py:150-183): one warp per game slot, the two half-warps score root
@@ -750,6 +880,7 @@ expectimax_play_kernel(const float *__restrict__ w, const uint32_t *__restrict__
                        int limit_tile, int step_limit, int depth, int width, int since_empty,
                        int8_t *__restrict__ trace_dir, uint16_t *__restrict__ trace_spawn, int64_t trace_len)
 {
+    __shared__ LfArena arena[4];
     const int64_t slot = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31, half = lane >> 4, hl = lane & 15;
     const unsigned hmask = 0xFFFFu << (lane & 16);
@@ -768,20 +899,30 @@ expectimax_play_kernel(const float *__restrict__ w, const uint32_t *__restrict__
             break;
         }
         const LfParams P{g.seed, id, odo, width, since_empty, &c_evals};
-        float val[2];
-#pragma unroll
-        for (int pass = 0; pass < 2; pass++) {
-            const int rd = 2 * pass + half;
-            uint32_t gain, fl;
-            const uint64_t a = move_dir(L, board, rd, gain, fl);
-            val[pass] = (fl & 3u) == 1u ? lf_top<N>(w, lut, a, depth, 4u + uint32_t(rd), P, hl, hmask) : -INFINITY;
-            __syncwarp();
-        }
         float v4[4];
-        v4[0] = __shfl_sync(FULL, val[0], 0);
-        v4[1] = __shfl_sync(FULL, val[0], 16);
-        v4[2] = __shfl_sync(FULL, val[1], 0);
-        v4[3] = __shfl_sync(FULL, val[1], 16);
+        if (depth >= 2) {                                                 // the whole warp on one root direction at a time
+#pragma unroll 1
+            for (int rd = 0; rd < 4; rd++) {
+                uint32_t gain, fl;
+                const uint64_t a = move_dir(L, board, rd, gain, fl);
+                v4[rd] = (fl & 3u) == 1u ? lf_top2<N>(w, lut, a, depth, 4u + uint32_t(rd), P, lane, arena[threadIdx.x >> 5])
+                                         : -INFINITY;
+            }
+        } else {                                                          // half-warps: root directions (0, 1) then (2, 3)
+            float val[2];
+#pragma unroll
+            for (int pass = 0; pass < 2; pass++) {
+                const int rd = 2 * pass + half;
+                uint32_t gain, fl;
+                const uint64_t a = move_dir(L, board, rd, gain, fl);
+                val[pass] = (fl & 3u) == 1u ? lf_top<N>(w, lut, a, depth, 4u + uint32_t(rd), P, hl, hmask) : -INFINITY;
+                __syncwarp();
+            }
+            v4[0] = __shfl_sync(FULL, val[0], 0);
+            v4[1] = __shfl_sync(FULL, val[0], 16);
+            v4[2] = __shfl_sync(FULL, val[1], 0);
+            v4[3] = __shfl_sync(FULL, val[1], 16);
+        }
         int bd = -1;
         float bv = -INFINITY;
 #pragma unroll
@@ -1747,7 +1888,7 @@ int look_forward_impl(const float *w, const uint32_t *lut, const uint64_t *board
                       const uint32_t *move_no, const uint8_t *root_dir, int64_t m, int depth, int width, int since_empty,
                       uint64_t seed, float *value, cudaStream_t st)
 {
-    look_forward_kernel<N><<<unsigned(cdiv(m * 16, 128)), 128, 0, st>>>(w, lut, boards, game_id, move_no, root_dir, m, depth,
+    look_forward_kernel<N><<<unsigned(cdiv(m * 32, 128)), 128, 0, st>>>(w, lut, boards, game_id, move_no, root_dir, m, depth,
                                                                        width, since_empty, seed, value);
     return launch_status();
 }

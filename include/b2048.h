@@ -202,7 +202,7 @@ int b2048_greedy_play(int n, const float *weights, const uint32_t *lut, const b2
  * The reference draws from Python's `random`; here every node draws node-keyed Philox words: key = seed, counter =
  * (id_lo, id_hi, move_no, purpose | path << 8), purpose 2 = positions, 3 = tiles, path = 4 + root_dir at the root
  * afterstate and path * 16 + 4 * tile_index + direction below it.  root_dir[q] = the direction that produced
- * afterstate q.  16 lanes per afterstate.  A direction that would create a 2^16 tile is skipped. */
+ * afterstate q.  One warp per afterstate.  A direction that would create a 2^16 tile is skipped. */
 int b2048_look_forward(int n, const float *weights, const uint32_t *lut, const uint64_t *boards, const uint64_t *game_id,
                        const uint32_t *move_no, const uint8_t *root_dir, int64_t m, int depth, int width, int since_empty,
                        uint64_t seed, float *value, b2048_stream_t stream);
