@@ -389,6 +389,18 @@ def td_extras(args, ctx, engine, cabi, wd):
         dt = timed(lambda: t2.run(256), 2)
         c1 = g2.read_counters()
         out[f"td_updates_per_sec_{name}"] = (c1["updates"] - c0["updates"]) / dt
+    # deterministic mode: the weights after 300 lock-steps from seeded weights, twice -- the checksum (xor and wrapping
+    # sum of the float bit patterns) is identical run to run (and equals the CPU oracle's, tests/test_gpu_full_size.py)
+    sums = []
+    for rep in range(2):
+        w3 = ctx.to_device(seeded_weights(n))
+        g4 = engine.GameBatch(B, seed=3, ctx=ctx).init()
+        engine.TDTrainer(ctx, n, w3, g4, args.alpha, cabi.UPD_DETERMINISTIC | cabi.UPD_MEAN).run(300)
+        bits = w3.view(torch.int32).to(torch.int64)
+        x = int(np.bitwise_xor.reduce(bits.cpu().numpy()))
+        sums.append(f"{x & 0xFFFFFFFF:08x}-{int(bits.sum().item()) & 0xFFFFFFFFFFFFFFFF:016x}")
+    out["deterministic_weights_checksum_300_locksteps"] = sums[0]
+    out["deterministic_checksum_repeat_equal"] = sums[0] == sums[1]
     # greedy play, BASELINE configs[0] shape: 1,000 seeded games to completion from the trained-so-far weights
     g3 = engine.GameBatch(1000, seed=2, ctx=ctx).init()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
