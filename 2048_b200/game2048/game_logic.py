@@ -79,50 +79,48 @@ def create_table():
 class Game:
     """:48-269"""
 
-    actions = {0: 'left', 1: 'up', 2: 'right', 3: 'down'}
+    actions = dict(enumerate(('left', 'up', 'right', 'down')))
     table = _MoveTable()
     counter = 0
     save_file = 'saved_game.pkl'
     _cache = (None, None)          # (packed board, its move4 result): pre_move is called 4x per position
 
     def __init__(self, score=0, row=None, file=None):
-        self.score = score
-        self.odometer = 0
-        self.moves = []
-        self.tiles = []
-        self.history = {}
-        if row is None:
-            self.row = np.zeros((4, 4), dtype=np.int32)
+        self.score, self.odometer = score, 0
+        self.moves, self.tiles, self.history = [], [], {}
+        self.file = file if file else Game.save_file
+        if row is not None:
+            self.row, self.starting_position = np.array(row, dtype=np.int32), row
+            return
+        self.row = np.zeros((4, 4), dtype=np.int32)
+        for _ in range(2):
             self.new_tile()
-            self.new_tile()
-            self.tiles = []                                  # the two initial spawns are not recorded (:65)
-            self.starting_position = self.row.copy()
-        else:
-            self.row = np.array(row, dtype=np.int32)
-            self.starting_position = row
-        self.file = file or Game.save_file
+        del self.tiles[:]                                    # the two initial spawns are not recorded (:65)
+        self.starting_position = self.row.copy()
 
     def copy(self):
-        return Game(self.score, self.row)
+        return Game(score=self.score, row=self.row)
 
     def save_game(self, file=None):
-        with open(file or self.file, 'wb') as f:
-            pickle.dump(self, f, -1)
+        with open(file or self.file, 'wb') as out:
+            pickle.dump(self, out, pickle.HIGHEST_PROTOCOL)
 
     @staticmethod
     def load_game(file=save_file):
-        with open(file, 'rb') as f:
-            return pickle.load(f)
+        with open(file, 'rb') as src:
+            return pickle.load(src)
 
     def __eq__(self, other):
-        return np.array_equal(self.row, other.row)
+        return bool((np.asarray(self.row) == np.asarray(other.row)).all())
 
     def __str__(self):
-        lines = []
-        for r in self.row:
-            lines.append(''.join(str(1 << v if v else 0) + '\t' * (4 if (1 << v) < 1000 else 3) for v in r))
-        return '\n'.join(lines) + f'\n score = {str(self.score)} moves = {str(self.odometer)} ' \
-                                  f'reached {1 << np.max(self.row)}'
+        def cell(v):
+            shown = (1 << int(v)) if v else 0
+            return f'{shown}' + '\t' * (3 if shown >= 1000 else 4)     # the reference's tab layout (:89-93)
+
+        body = [''.join(cell(v) for v in line) for line in self.row]
+        body.append(f' score = {self.score} moves = {self.odometer} reached {1 << np.max(self.row)}')
+        return '\n'.join(body)
 
     # ------------------------------------------------------------------ device helpers
     @staticmethod
@@ -146,8 +144,8 @@ class Game:
     # ------------------------------------------------------------------ board predicates (:96-110)
     @staticmethod
     def empty(row):
-        _, mask = Game._stats(row)
-        return [(p // 4, p % 4) for p in range(16) if (mask >> p) & 1]
+        mask = Game._stats(row)[1]
+        return [divmod(p, 4) for p in range(16) if mask & (1 << p)]
 
     @staticmethod
     def empty_count(row):
@@ -162,76 +160,81 @@ class Game:
 
     # ------------------------------------------------------------------ spawns (:112-121)
     def create_new_tile(self, row):
-        em = self.empty(row)
-        tile = 1 if random.randrange(10) else 2
-        position = random.choice(em)
-        return tile, position
+        """consumes `random` in the reference's order: randrange(10) for the tile, then choice over the empties"""
+        cells = self.empty(row)
+        four = random.randrange(10) == 0
+        return (2 if four else 1), random.choice(cells)
 
     def new_tile(self):
-        tile, position = self.create_new_tile(self.row)
-        self.row[position] = tile
-        self.tiles.append((tile, position))
+        spawn = self.create_new_tile(self.row)
+        self.row[spawn[1]] = spawn[0]
+        self.tiles.append(spawn)
 
     # ------------------------------------------------------------------ moves (:123-148)
+    _OVERFLOW = 'a 2^16 tile cannot be represented (the reference raises KeyError on its next move)'
+
     @staticmethod
     def _left(row, score):
         after, gain, flags = Game._move4(row)
-        change = bool(flags & 1)
         if flags & 16:
-            raise OverflowError('a 2^16 tile cannot be represented (the reference raises KeyError on its next move)')
-        return unpack_board(after[0]), score + int(gain[0]), change
+            raise OverflowError(Game._OVERFLOW)
+        return unpack_board(after[0]), score + int(gain[0]), bool(flags & 1)
 
     def pre_move(self, row, score, direction):
         Game.counter += 1
         after, gain, flags = Game._move4(row)
-        if (flags >> (4 + direction)) & 1:
-            raise OverflowError('a 2^16 tile cannot be represented (the reference raises KeyError on its next move)')
-        change = bool((flags >> direction) & 1)
+        if flags & (16 << direction):
+            raise OverflowError(Game._OVERFLOW)
         # the reference adds the line scores only for changed lines, which is all lines with a merge
-        return unpack_board(after[direction]), score + int(gain[direction]), change
+        return unpack_board(after[direction]), score + int(gain[direction]), bool(flags & (1 << direction))
 
     def make_move(self, direction):
-        self.row, self.score, change = self.pre_move(self.row, self.score, direction)
-        self.odometer += 1
+        moved = self.pre_move(self.row, self.score, direction)
+        self.row, self.score = moved[0], moved[1]
+        self._count_move(direction)
+        return moved[2]
+
+    def _count_move(self, direction):
         self.moves.append(direction)
-        return change
+        self.odometer += 1
 
     # ------------------------------------------------------------------ greedy play (:150-211)
+    def _device_look_forward(self, agent, valid, depth, width, since_empty):
+        """all look_forward trees of one move in one kernel (b2048_look_forward, node-keyed Philox draws):
+        {direction: value} for the changed directions in `valid`"""
+        if not valid:
+            return {}
+        ctx = engine.Context.get()
+        if not hasattr(self, '_lf_seed'):
+            self._lf_seed = random.getrandbits(63)
+        k = len(valid)
+        boards = ctx.to_device(np.array([pack_row(c[1]) for c in valid], dtype=np.uint64))
+        vals = ctx.look_forward(agent.n, agent._device_weights(), boards,
+                                ctx.to_device(np.zeros(k, dtype=np.uint64)),
+                                ctx.to_device(np.full(k, self.odometer, dtype=np.uint32)),
+                                ctx.to_device(np.array([c[0] for c in valid], dtype=np.uint8)), depth, width,
+                                since_empty, seed=self._lf_seed).cpu().numpy()
+        return {c[0]: float(v) for c, v in zip(valid, vals)}
+
     def _find_best_move(self, estimator, depth, width, since_empty):
-        best_dir, best_value = 0, -np.inf
-        best_row, best_score = None, None
-        agent = self._agent_of(estimator) if depth > 0 else None
+        """(direction, afterstate, score) of the best changed direction; strict '>' so the lowest direction wins
+        ties, direction 0 with no afterstate when nothing moves (:150-161)"""
         cand = [(d,) + tuple(self.pre_move(self.row, self.score, d)) for d in range(4)]
-        device_values = {}
-        if agent is not None and 1 <= width <= 4 and depth <= 4:
-            # all look_forward trees of the move in one kernel (b2048_look_forward, node-keyed Philox draws);
-            # other estimators / parameters keep the reference's host recursion on Python's `random`
-            ctx = engine.Context.get()
-            valid = [c for c in cand if c[3]]
-            if valid:
-                if not hasattr(self, '_lf_seed'):
-                    self._lf_seed = random.getrandbits(63)
-                boards = ctx.to_device(np.array([pack_row(c[1]) for c in valid], dtype=np.uint64))
-                k = len(valid)
-                vals = ctx.look_forward(agent.n, agent._device_weights(), boards,
-                                        ctx.to_device(np.zeros(k, dtype=np.uint64)),
-                                        ctx.to_device(np.full(k, self.odometer, dtype=np.uint32)),
-                                        ctx.to_device(np.array([c[0] for c in valid], dtype=np.uint8)), depth, width,
-                                        since_empty, seed=self._lf_seed).cpu().numpy()
-                device_values = {c[0]: float(v) for c, v in zip(valid, vals)}
-        for direction, new_row, new_score, change in cand:
-            if not change:
-                continue
-            value = device_values[direction] if direction in device_values else \
-                self.look_forward(estimator, new_row, new_score, depth=depth, width=width, since_empty=since_empty)
-            if value > best_value:                           # strict: the lowest direction wins ties
-                best_dir, best_value = direction, value
-                best_row, best_score = new_row, new_score
-        return best_dir, best_row, best_score
+        valid = [c for c in cand if c[3]]
+        agent = self._agent_of(estimator) if depth > 0 else None
+        on_device = agent is not None and 1 <= width <= 4 and depth <= 4
+        # other estimators / parameters keep the reference's host recursion on Python's `random`
+        values = self._device_look_forward(agent, valid, depth, width, since_empty) if on_device else {}
+        pick, top = (0, None, None), -np.inf
+        for d, after, gained, _ in valid:
+            v = values[d] if d in values else self.look_forward(estimator, after, gained, depth=depth, width=width,
+                                                                since_empty=since_empty)
+            if v > top:
+                pick, top = (d, after, gained), v
+        return pick
 
     def _move_on(self, best_dir, best_row, best_score):
-        self.moves.append(best_dir)
-        self.odometer += 1
+        self._count_move(best_dir)
         self.row, self.score = best_row, best_score
         self.new_tile()
 
@@ -243,25 +246,31 @@ class Game:
             return owner
         return None
 
+    def _decisions(self, estimator, limit_tile, depth, width, since_empty, step_limit=None):
+        """the reference's three play loops (:170-211) share this generator: yields the chosen
+        (direction, afterstate, score) while the game can go on; the caller applies it with _move_on.
+        Returns True if the game ended because no move was left."""
+        while step_limit is None or self.odometer < step_limit:
+            if self.game_over(self.row):
+                return True
+            if limit_tile and self.row.max() >= limit_tile:
+                return False
+            yield self._find_best_move(estimator, depth, width, since_empty)
+        return False
+
     def trial_run(self, estimator, limit_tile=0, step_limit=100000, depth=0, width=1, since_empty=0, verbose=False):
         """:170-183.  With an agent's evaluate() and depth 0 the whole game runs in one kernel
         (b2048_greedy_play, Philox spawns keyed by a draw from `random`); otherwise the reference's loop."""
         agent = self._agent_of(estimator)
         if agent is not None and depth == 0 and not verbose:
             return self._trial_run_device(agent, limit_tile, step_limit)
-        if verbose:
-            print('Starting position:')
-            print(self)
-        while self.odometer < step_limit:
-            if self.game_over(self.row):
-                return
-            if limit_tile and np.max(self.row) >= limit_tile:
-                break
-            best_dir, best_row, best_score = self._find_best_move(estimator, depth, width, since_empty)
-            self._move_on(best_dir, best_row, best_score)
-            if verbose:
-                print(f'On {self.odometer} we moved {Game.actions[best_dir]}')
-                print(self)
+        say = print if verbose else (lambda *a: None)
+        say('Starting position:')
+        say(self)
+        for choice in self._decisions(estimator, limit_tile, depth, width, since_empty, step_limit):
+            self._move_on(*choice)
+            say(f'On {self.odometer} we moved {Game.actions[choice[0]]}')
+            say(self)
 
     def _trial_run_device(self, agent, limit_tile, step_limit, trace_len=1 << 15):
         ctx = engine.Context.get()
@@ -287,85 +296,65 @@ class Game:
 
     def trial_run_for_thread(self, estimator, depth=0, width=1, since_empty=0, stopper=None):
         """:186-197 (Dash 'Agent Play'): same loop, records history, polls the stop flag"""
-        parent, this_thread = stopper['parent'], stopper['n']
-        while True:
-            if GAME_PANE[parent]['id'] != this_thread:  # noqa: F405
-                return
-            if self.game_over(self.row):
-                self.history[self.odometer] = (self.row.copy(), self.score, -1)
+        owner, ticket = stopper['parent'], stopper['n']
+        plan = self._decisions(estimator, 0, depth, width, since_empty)
+        while GAME_PANE[owner]['id'] == ticket:  # noqa: F405
+            choice = next(plan, None)
+            snapshot = (self.row.copy(), self.score, -1 if choice is None else choice[0])
+            self.history[self.odometer] = snapshot
+            if choice is None:
                 self.moves.append(-1)
-                return
-            best_dir, best_row, best_score = self._find_best_move(estimator, depth, width, since_empty)
-            self.history[self.odometer] = (self.row.copy(), self.score, best_dir)
-            self._move_on(best_dir, best_row, best_score)
+                break
+            self._move_on(*choice)
 
     def thread_trial(self, *args, **kwargs):
         Thread(target=self.trial_run_for_thread, args=args, kwargs=kwargs, daemon=True).start()
 
     def generate_run(self, estimator, limit_tile=0, depth=0, width=1, since_empty=16):
         """:203-211 (show.py)"""
-        while True:
-            if self.game_over(self.row):
-                return
-            if limit_tile and np.max(self.row) >= limit_tile:
-                break
-            best_dir, best_row, best_score = self._find_best_move(estimator, depth, width, since_empty)
-            yield self, best_dir
-            self._move_on(best_dir, best_row, best_score)
+        for choice in self._decisions(estimator, limit_tile, depth, width, since_empty):
+            yield self, choice[0]
+            self._move_on(*choice)
 
     # ------------------------------------------------------------------ look-ahead (:214-243)
     def look_forward(self, estimator, row, score, depth, width, since_empty):
-        """depth 0 is the hot path (estimator call); depth > 0 is the reference's sampled expectimax, kept on
-        the host on top of the GPU board primitives ('next', not yet batched)"""
-        if depth == 0:
+        """the reference's sampled expectimax on the host, on top of the GPU board primitives; used for
+        estimators that are not a QAgent (agents go through _device_look_forward).  Draw order on `random`
+        as in the reference: one sample() of the positions, then one randrange(10) per position."""
+        room = self.empty_count(row) if depth else 0
+        if depth == 0 or room >= since_empty:
             return estimator(row, score)
-        empty = self.empty_count(row)
-        if empty >= since_empty:
-            return estimator(row, score)
-        num_tiles = min(width, empty)
-        tile_positions = random.sample(self.empty(row), num_tiles)
-        average = 0
-        for position in tile_positions:
-            new_tile = 1 if random.randrange(10) else 2
-            new_row = row.copy()
-            new_row[position] = new_tile
-            if self.game_over(new_row):
-                best_value = -100
-            else:
-                best_value = -np.inf
-                for direction in range(4):
-                    test_row, test_score, change = self.pre_move(new_row, score, direction)
-                    if change:
-                        value = self.look_forward(estimator, test_row, test_score, depth=depth - 1, width=width,
-                                                  since_empty=since_empty)
-                        best_value = max(best_value, value)
-            average += max(best_value, 0)
-        return average / num_tiles
+        spots = random.sample(self.empty(row), min(width, room))
+        total = 0
+        for spot in spots:
+            child = row.copy()
+            child[spot] = 1 if random.randrange(10) else 2
+            if self.game_over(child):
+                continue                                     # max(-100, 0) adds nothing (:231, :242)
+            replies = (self.pre_move(child, score, d) for d in range(4))
+            below = [self.look_forward(estimator, r, s, depth=depth - 1, width=width, since_empty=since_empty)
+                     for r, s, ok in replies if ok]
+            total += max(max(below), 0)
+        return total / len(spots)
 
     # ------------------------------------------------------------------ replay (:245-269)
     def replay(self, verbose=True):
         """rebuild the chain of boards from starting_position, moves and tiles.  Unlike the reference this does
         not need a trailing -1 in moves (trial_run does not append one, :267 would raise IndexError there)."""
+        say = print if verbose else (lambda *a: None)
+        ghost = Game(row=self.starting_position)
+        say('Starting position:')
+        say(ghost)
         chain = {}
-        replay_game = Game(row=self.starting_position)
-        if verbose:
-            print('Starting position:')
-            print(replay_game)
-        for i in range(self.odometer):
-            move = self.moves[i]
-            chain[i] = (replay_game.row.copy(), replay_game.score, move)
-            new_tile, position = self.tiles[i]
-            if verbose:
-                print(i, new_tile, position)
-            replay_game.make_move(move)
-            replay_game.row[position] = new_tile
-            if verbose:
-                print(f'On {replay_game.odometer} we move = {Game.actions[move]}, '
-                      f'new tile = {new_tile} at position = {position}')
-                print(replay_game)
-        if verbose:
-            print('no more moves possible, final position')
-        last = self.moves[self.odometer] if len(self.moves) > self.odometer else -1
-        chain[self.odometer] = (self.row.copy(), self.score, last)
-        chain[self.odometer + 1] = (None, None, -1)
+        n = self.odometer
+        for i, (move, (tile, where)) in enumerate(zip(self.moves[:n], self.tiles[:n])):
+            chain[i] = (ghost.row.copy(), ghost.score, move)
+            say(i, tile, where)
+            ghost.make_move(move)
+            ghost.row[where] = tile
+            say(f'On {ghost.odometer} we move = {Game.actions[move]}, new tile = {tile} at position = {where}')
+            say(ghost)
+        say('no more moves possible, final position')
+        chain[n] = (self.row.copy(), self.score, self.moves[n] if len(self.moves) > n else -1)
+        chain[n + 1] = (None, None, -1)
         return chain

@@ -26,14 +26,32 @@ from collections import deque
 
 
 def check_thread(parent, benchmark):
-    """:6-13 heartbeat of the Dash session that owns a worker thread"""
+    """:6-13 heartbeat of the Dash session that owns a worker thread: once two check intervals have passed, the
+    session must have raised its RUNNING flag again, else 0 tells the worker to stop; the flag is cleared and
+    the clock restarted otherwise"""
     now = time.time()
-    if (now - benchmark) > 2 * dash_intervals['check_run']:
-        if RUNNING[parent] == 0:
-            return 0
-        RUNNING[parent] = 0
-        return now
-    return benchmark
+    if now - benchmark <= 2 * dash_intervals['check_run']:
+        return benchmark
+    alive, RUNNING[parent] = RUNNING[parent], 0
+    return now if alive else 0
+
+
+class _Owner:
+    """the `stopper` protocol of the Dash front end (:280-290, :362-369): {'parent': session, 'a': ticket}.
+    go_on() is False once another job took the agent pane; lost() is True when the session stopped pinging."""
+
+    def __init__(self, stopper):
+        self.session = stopper['parent'] if stopper else None
+        self.ticket = stopper['a'] if stopper else None
+        self.clock = time.time()
+
+    def go_on(self):
+        return self.session is None or AGENT_PANE[self.session]['id'] == self.ticket
+
+    def lost(self):
+        if self.session is not None:
+            self.clock = check_thread(self.session, self.clock)
+        return not self.clock
 
 
 def _features(n, x):
@@ -70,40 +88,34 @@ def f_6(x):
 class QAgent:
     """:85-406"""
 
-    feature_functions = {2: f_2, 3: f_3, 4: f_4, 5: f_5, 6: f_6}
-    parameter_shape = {2: (24, 16 ** 2), 3: (52, 16 ** 3), 4: (17, 16 ** 4), 5: (21, 16 ** 5), 6: (33, 0)}
+    feature_functions = dict(zip(range(2, 7), (f_2, f_3, f_4, f_5, f_6)))
+    parameter_shape = {2: (24, 1 << 8), 3: (52, 1 << 12), 4: (17, 1 << 16), 5: (21, 1 << 20), 6: (33, 0)}
 
     def __init__(self, name='agent', config_file=None, storage='s3', console='web', log_file=None, n=4, alpha=0.25,
                  decay=0.75, decay_step=10000, low_alpha_limit=0.01, with_weights=True,
                  batch=1024, update_mode='atomic', seed=None):
-        self.name = name
-        self.file = name + '.pkl'
-        self.game_file = 'best_of_' + self.file
-        self.s3 = (storage == 's3')
+        self.name, self.file = name, f'{name}.pkl'
+        self.game_file = f'best_of_{self.file}'
+        self.s3 = storage == 's3'
         self.log_file = log_file
-        self.print = print if (console == 'local' or log_file is None) else Logger(log_file=log_file).add
+        quiet_web = console != 'local' and log_file is not None
+        self.print = Logger(log_file=log_file).add if quiet_web else print
 
-        config = (load_s3(config_file) or {}) if config_file else {}
-        self.n = config.get('n', n)
-        self.alpha = config.get('alpha', alpha)
-        self.decay = config.get('decay', decay)
-        self.decay_step = config.get('decay_step', decay_step)
-        self.low_alpha_limit = config.get('low_alpha_limit', low_alpha_limit)
-
+        # hyper-parameters: the stored config (if any) overrides the arguments (:104-113)
+        stored = (load_s3(config_file) if config_file else None) or {}
+        given = dict(n=n, alpha=alpha, decay=decay, decay_step=decay_step, low_alpha_limit=low_alpha_limit)
+        for key, value in given.items():
+            setattr(self, key, stored.get(key, value))
         self.num_feat, self.size_feat = QAgent.parameter_shape[self.n]
         self.features = QAgent.feature_functions[self.n]
 
-        self.step = 0
-        self.top_game = None
-        self.top_score = 0
-        self.train_history = []
+        # training state (:119-125)
+        self.step, self.top_score, self.top_tile = 0, 0, 10
+        self.top_game, self.train_history = None, []
         self.next_decay = self.decay_step
-        self.top_tile = 10
 
         # new knobs (not in the reference): games per lock-step, scatter mode, Philox seed
-        self.batch = batch
-        self.update_mode = update_mode
-        self.seed = seed
+        self.batch, self.update_mode, self.seed = batch, update_mode, seed
 
         self._w = None                      # float32 device buffer (never pickled)
         self.weights = None                 # file-format arrays, only between load and first use
@@ -112,7 +124,8 @@ class QAgent:
             self.init_weights()
 
     def __str__(self):
-        return f'Agent {self.name}, n={self.n}\ntrained for {self.step} episodes, top score = {self.top_score}'
+        return '\n'.join((f'Agent {self.name}, n={self.n}',
+                          f'trained for {self.step} episodes, top score = {self.top_score}'))
 
     # ------------------------------------------------------------------ weights (:136-164)
     def init_weights(self):
@@ -171,36 +184,34 @@ class QAgent:
 
     # ------------------------------------------------------------------ save / load (:166-200)
     def save_agent(self):
-        if self.s3:
-            nps = self.list_to_np()
-            agent_params = QAgent(name=self.name, with_weights=False)
-            for key in self.__dict__:
-                if key not in ('weights', '_w'):
-                    setattr(agent_params, key, getattr(self, key))
-            save_s3(agent_params, 'a/' + self.file)
-            save_s3(nps, 'weights/' + self.file)
-        else:
-            with open(self.file, 'wb') as f:
-                pickle.dump(self, f, -1)
+        """S3 layout as the reference: the agent without weights under a/, the weight arrays under weights/"""
+        if not self.s3:
+            with open(self.file, 'wb') as out:
+                pickle.dump(self, out, pickle.HIGHEST_PROTOCOL)
+            return
+        shell = QAgent(name=self.name, with_weights=False)
+        shell.__dict__.update({k: v for k, v in self.__dict__.items() if k not in ('weights', '_w')})
+        save_s3(shell, f'a/{self.file}')
+        save_s3(self.list_to_np(), f'weights/{self.file}')
 
     def save_game(self, game):
-        if self.s3:
-            save_s3(game, 'g/' + self.game_file)
-        else:
-            game.save_game(self.game_file)
+        if not self.s3:
+            return game.save_game(self.game_file)
+        save_s3(game, f'g/{self.game_file}')
 
     @staticmethod
     def load_agent_local(file):
         """:188-193 (the reference opens the pickle in text mode, which cannot work on Python 3; fixed)"""
-        with open(file, 'rb') as f:
-            agent = pickle.load(f)
+        with open(file, 'rb') as src:
+            agent = pickle.load(src)
         agent.np_to_list()
         return agent
 
     @staticmethod
     def load_agent(file):
+        """:195-200 `file` is the S3 key 'a/<name>.pkl'; its weights sit under 'weights/<name>.pkl'"""
         agent = load_s3(file)
-        agent.weights = load_s3(f'weights/{file[2:]}')
+        agent.weights = load_s3('weights/' + file[2:])
         agent.np_to_list()
         return agent
 
@@ -256,13 +267,52 @@ class QAgent:
 
     def decay_alpha(self):
         """:257-262"""
-        self.alpha = round(max(self.alpha * self.decay, self.low_alpha_limit), 4)
-        self.next_decay = self.step + self.decay_step
-        self.print('------')
+        decayed = max(self.alpha * self.decay, self.low_alpha_limit)
+        self.alpha, self.next_decay = round(decayed, 4), self.step + self.decay_step
+        rule = '-' * 6
+        self.print(rule)
         self._display_lr()
-        self.print('------')
+        self.print(rule)
 
     # ------------------------------------------------------------------ train_run (:269-346)
+    def _account(self, i, game, max_tile, book, saving):
+        """the reference's per-episode statistics, reports and save cadence (:298-341) for episode number i"""
+        book['ma100'].append(game.score)
+        book['last1000'].append(game.score)
+        if game.score > book['best'].score:
+            book['best'] = game
+            if game.score > self.top_score:
+                self.top_game, self.top_score = game, game.score
+                self.print(f'\nnew best game at episode {i}!\n{game}\n')
+                if saving:
+                    self.save_game(game)
+                    self.print(f'game saved at {self.game_file}')
+        if max_tile >= 10:
+            book['reached'][min(max_tile, 16) - 10] += 1
+        if max_tile > self.top_tile:                       # a new maximum tile also decays the learning rate
+            self.top_tile = max_tile
+            self.decay_alpha()
+        if i % 100 == 0:
+            ma = int(np.mean(book['ma100']))
+            self.train_history.append(ma)
+            self.print(f'episode {i}: score {game.score} reached {1 << max_tile} ma_100 = {ma}')
+        if i % 1000:
+            return
+        now = time.time()
+        lines = ['\n------', f'{round((now - book["lap"]) / 60, 2)} min', f'episode = {i}',
+                 f'average over last 1000 episodes = {np.mean(book["last1000"])}']
+        tail_counts = np.cumsum(book['reached'][::-1])[::-1] / 10          # share (%) reaching >= 2^(10+j)
+        lines += [f'{1 << (j + 10)} reached in {float(r)} %' for j, r in enumerate(tail_counts) if r]
+        lines += ['best of last 1000:', str(book['best']), 'best of this Agent:', str(self.top_game)]
+        for line in lines:
+            self.print(line)
+        self._display_lr()
+        self.print('------\n')
+        if saving:
+            self.save_agent()
+            self.print(f'agent saved in {self.file}')
+        book.update(lap=now, last1000=[], reached=[0] * 7, best=Game(row=np.zeros((4, 4), dtype=np.int32)))
+
     def train_run(self, num_eps=100000, add_weights='already', saving=True, stopper=None, batch=None, chunk=64):
         """Same driver as the reference (episode statistics, learning-rate decay, report and save cadence), with
         `batch` games advancing in lock-step on the GPU; episodes are accounted in completion order."""
@@ -272,84 +322,32 @@ class QAgent:
             self.print('loading weights ...')
             self.weights = load_s3(add_weights)
             self.np_to_list()
-        if stopper:
-            parent, this_thread = stopper['parent'], stopper['a']
+        owner = _Owner(stopper)
         B = int(batch or self.batch)
         ctx = engine.Context.get()
         games = engine.GameBatch(B, seed=self._next_seed(), ctx=ctx, fin_cap=max(4 * B, 4096)).init(first_id=self.step)
         tr = engine.TDTrainer(ctx, self.n, self._device_weights(), games, self.alpha, self._mode(B))
-        av1000, ma100 = [], deque(maxlen=100)
-        reached = [0] * 7
-        best_of_1000 = Game(row=np.zeros((4, 4), dtype=np.int32))
-        global_start = start = benchmark_time = time.time()
+        began = time.time()
+        book = dict(ma100=deque(maxlen=100), last1000=[], reached=[0] * 7, lap=began,
+                    best=Game(row=np.zeros((4, 4), dtype=np.int32)))
         self.print(f'Agent {self.name} training session started, current step = {self.step}')
         self.print('Agent will be saved every 1000 episodes and on STOP command')
-        first, last = self.step + 1, self.step + num_eps + 1          # the reference runs num_eps + 1 episodes (:284)
-        i = first - 1
-        stop = False
-        while i < last and not stop:
-            if stopper:
-                if AGENT_PANE[parent]['id'] != this_thread:
-                    break
-                benchmark_time = check_thread(parent, benchmark_time)
-                if not benchmark_time:
-                    return
+        i, last = self.step, self.step + num_eps + 1       # the reference runs num_eps + 1 episodes (:284)
+        while i < last and owner.go_on():
+            if owner.lost():
+                return
             tr.alpha = float(self.alpha)
             tr.run(chunk)
-            for rec in games.drain_finished():
+            for rec in games.drain_finished()[:last - i]:
                 i += 1
-                if i > last:
-                    break
                 if self.step > self.next_decay and self.alpha > self.low_alpha_limit:
                     self.decay_alpha()
                 self.step += 1
-                score, odo, max_tile = int(rec[2]), int(rec[3]), int(rec[4])
-                game = Game(score=score, row=unpack_board((int(rec[6]) << 32) | int(rec[5])))
-                game.odometer = odo
-                ma100.append(score)
-                av1000.append(score)
-                if score > best_of_1000.score:
-                    best_of_1000 = game
-                    if score > self.top_score:
-                        self.top_game, self.top_score = game, score
-                        self.print(f'\nnew best game at episode {i}!\n{game.__str__()}\n')
-                        if saving:
-                            self.save_game(game)
-                            self.print(f'game saved at {self.game_file}')
-                if max_tile >= 10:
-                    reached[min(max_tile, 16) - 10] += 1
-                if max_tile > self.top_tile:
-                    self.top_tile = max_tile
-                    self.decay_alpha()
-                if i % 100 == 0:
-                    ma = int(np.mean(ma100))
-                    self.train_history.append(ma)
-                    self.print(f'episode {i}: score {score} reached {1 << max_tile} ma_100 = {ma}')
-                if i % 1000 == 0:
-                    average = np.mean(av1000)
-                    self.print('\n------')
-                    self.print(f'{round((time.time() - start) / 60, 2)} min')
-                    start = time.time()
-                    self.print(f'episode = {i}')
-                    self.print(f'average over last 1000 episodes = {average}')
-                    av1000 = []
-                    for j in range(7):
-                        r = sum(reached[j:]) / 10
-                        if r:
-                            self.print(f'{1 << (j + 10)} reached in {r} %')
-                    reached = [0] * 7
-                    self.print('best of last 1000:')
-                    self.print(best_of_1000.__str__())
-                    self.print('best of this Agent:')
-                    self.print(self.top_game.__str__())
-                    self._display_lr()
-                    self.print('------\n')
-                    if saving:
-                        self.save_agent()
-                        self.print(f'agent saved in {self.file}')
-                    best_of_1000 = Game(row=np.zeros((4, 4), dtype=np.int32))
-        total_time = int(time.time() - global_start)
-        self.print(f'Total time = {total_time // 60} min {total_time % 60} sec')
+                game = Game(score=int(rec[2]), row=unpack_board((int(rec[6]) << 32) | int(rec[5])))
+                game.odometer = int(rec[3])
+                self._account(i, game, int(rec[4]), book, saving)
+        spent = int(time.time() - began)
+        self.print(f'Total time = {spent // 60} min {spent % 60} sec')
         if saving:
             self.save_agent()
             self.print(f'{self.name} saved at step {self.step} in {self.file}\n------------------------\n')
@@ -357,63 +355,53 @@ class QAgent:
 
     # ------------------------------------------------------------------ trial (:348-406)
     @staticmethod
+    def _trial_report(results, elapsed, shuffles):
+        """the reference's summary text (:384-399); `results` sorted by score, best first"""
+        reached = np.array([1 << int(np.max(g.row)) for g in results])
+        moves = max(sum(g.odometer for g in results), 1)
+        parts = ['\nBest games:'] + [f'{g}\n' for g in results[:3]]
+        parts.append(f'average score of {len(results)} runs = {np.average([g.score for g in results])}')
+        parts += [f'{tile} reached in {np.count_nonzero(reached >= tile) / len(results) * 100}%'
+                  for tile in (16384, 8192, 4096, 2048, 1024)]
+        parts += [f'total time = {round(elapsed, 2)}',
+                  f'average time per move = {round(elapsed / moves * 1000, 4)} ms',
+                  f'total number of shuffles = {Game.counter}',
+                  f'time per shuffle = {round(elapsed / max(shuffles, 1) * 1000, 4)} ms']
+        return '\n'.join(parts)
+
+    @staticmethod
     def trial(estimator=None, agent_file=None, limit_tile=0, num=20, game_init=None, depth=0, width=1, since_empty=6,
               storage='s3', console='local', log_file=None, game_file=None, verbose=False, stopper=None, seed=None):
-        display = print if console == 'local' else Logger(log_file=log_file).add
-        if stopper:
-            parent, this_thread = stopper['parent'], stopper['a']
-        agent = None
+        display = Logger(log_file=log_file).add if console != 'local' else print
+        owner = _Owner(stopper)
         if agent_file:
             display(f'Loading Agent from {agent_file} ...')
             agent = QAgent.load_agent(agent_file)
             estimator = agent.evaluate
             display(f'Trial run for {num} games, Agent = {agent.name}\n'
                     f'Looking forward: depth={depth}, width={width}, since_empty={since_empty}')
-        elif estimator is not None:
-            agent = Game._agent_of(None, estimator)
-        start = benchmark_time = time.time()
-        counter0 = Game.counter
-        results = []
-        if agent is not None and not verbose and not stopper and depth <= 4 and (depth == 0 or 1 <= width <= 4):
+        else:
+            agent = Game._agent_of(None, estimator) if estimator is not None else None
+        began, counter0 = time.time(), Game.counter
+        batched = agent is not None and not (verbose or stopper) and depth <= 4 and (depth == 0 or 1 <= width <= 4)
+        if batched:
             results = QAgent._trial_device(agent, num, limit_tile, game_init, seed, display, depth, width, since_empty)
         else:
-            for i in range(num):
-                if stopper:
-                    if AGENT_PANE[parent]['id'] != this_thread:
-                        break
-                    benchmark_time = check_thread(parent, benchmark_time)
-                    if not benchmark_time:
-                        return
-                now = time.time()
-                game = Game() if game_init is None else game_init.copy()
-                game.trial_run(estimator, limit_tile=limit_tile, depth=depth, width=width, since_empty=since_empty,
-                               verbose=verbose)
-                display(f'game {i}, result {game.score}, moves {game.odometer}, achieved {1 << np.max(game.row)}, '
-                        f'time = {(time.time() - now):.2f}')
+            results = []
+            look = dict(limit_tile=limit_tile, depth=depth, width=width, since_empty=since_empty, verbose=verbose)
+            while len(results) < num and owner.go_on():
+                if owner.lost():
+                    return
+                t0 = time.time()
+                game = game_init.copy() if game_init is not None else Game()
+                game.trial_run(estimator, **look)
+                display(f'game {len(results)}, result {game.score}, moves {game.odometer}, '
+                        f'achieved {1 << np.max(game.row)}, time = {(time.time() - t0):.2f}')
                 results.append(game)
         if not results:
             return
-        average = np.average([v.score for v in results])
-        figures = [(1 << np.max(v.row)) for v in results]
-        total_odo = sum([v.odometer for v in results])
-        results.sort(key=lambda v: v.score, reverse=True)
-
-        def share(limit):
-            return len([0 for v in figures if v >= limit]) / len(figures) * 100
-
-        message = '\nBest games:\n'
-        for v in results[:3]:
-            message += v.__str__() + '\n' + '\n'
-        elapsed = time.time() - start
-        shuffles = max(Game.counter - counter0, 1)
-        message += f'average score of {len(results)} runs = {average}\n' + \
-                   f'16384 reached in {share(16384)}%\n' + f'8192 reached in {share(8192)}%\n' + \
-                   f'4096 reached in {share(4096)}%\n' + f'2048 reached in {share(2048)}%\n' + \
-                   f'1024 reached in {share(1024)}%\n' + f'total time = {round(elapsed, 2)}\n' + \
-                   f'average time per move = {round(elapsed / max(total_odo, 1) * 1000, 4)} ms\n' + \
-                   f'total number of shuffles = {Game.counter}\n' + \
-                   f'time per shuffle = {round(elapsed / shuffles * 1000, 4)} ms'
-        display(message)
+        results.sort(key=lambda g: -g.score)
+        display(QAgent._trial_report(results, time.time() - began, Game.counter - counter0))
         if game_file:
             if storage == 's3':
                 save_s3(results[0], game_file)
