@@ -298,6 +298,30 @@ def test_greedy_philox_vs_oracle(eng, orc, fx, n):
     assert np.array_equal(lim.to_host()["board"], ref_l["boards"])
 
 
+@pytest.mark.parametrize("n", [3, 4, 6])
+def test_gpu_philox_games_replay_through_reference_rules(eng, orc, fx, n):
+    """Reverse direction of the replay protocol: games the GPU played on its own Philox spawns,
+    recorded as (starting_position, moves, tiles) like a reference Game, are re-played by the oracle's
+    teacher-forced trial_run (pinned to the reference's recorded games in test_oracle_golden): it must choose
+    the same move at every step and end on the same board and score."""
+    ctx, engine, cabi = eng
+    w, wd = w_dev(ctx, fx, n, 13)
+    num, L = 20, 6000
+    games = engine.GameBatch(num, seed=77, ctx=ctx).init(first_id=500)
+    starts = games.to_host()["board"].copy()
+    tdir, _, tsp = engine.greedy_play(ctx, n, wd, games, trace_len=L)
+    h = games.to_host()
+    tdir, tsp = tdir.cpu().numpy(), tsp.cpu().numpy().view(np.uint16)
+    for j in range(num):
+        odo = int(h["moves"][j])
+        assert 0 < odo < L
+        tiles = [(int(s >> 8), (int(s & 15) // 4, int(s & 15) % 4)) for s in tsp[j, :odo]]
+        ref = orc.trial_replay(n, w, orc.unpack_np(starts[j:j + 1])[0], tiles)
+        assert ref["odometer"] == odo and ref["score"] == int(h["score"][j])
+        assert np.array_equal(ref["moves"], tdir[j, :odo].astype(np.int32))
+        assert np.array_equal(orc.pack_np(ref["row"][None].astype(np.int32))[0], h["board"][j])
+
+
 def _run_replay_episodes(ctx, engine, cabi, orc, g, n, wd, mode, episodes):
     out = []
     for i in range(episodes):
