@@ -1017,13 +1017,20 @@ __device__ __forceinline__ void slot_store(const b2048_games_t &g, int64_t slot,
 // One lock-step of one slot (QAgent.episode body, r_learning.py:228-249) on the register copy `s`: returns true if
 // the slot was live (its state changed); (ub, dw) = the TD update to apply (dw = NaN: none).  4 lanes per slot
 // (lane d = direction d); all 32 lanes of a warp must call this together (width-4 shuffles inside).
-template <int N, bool COHERENT>
+struct NoPublish {
+    __device__ __forceinline__ void operator()(uint64_t, float) const {}
+};
+
+// `publish(ub, dw)` is called by every lane as soon as the update of the step is known (afterstate to update and
+// dw; the bookkeeping, the restart and the spawn follow): the persistent kernel hands them to phase B there.
+template <int N, bool COHERENT, class Publish = NoPublish>
 __device__ __forceinline__ bool phase_a_compute(const float *__restrict__ w, const LutGlobal &L, const b2048_games_t &g,
                                                 float alpha, int64_t slot, int d, bool in, SlotState &s, uint64_t &ub,
                                                 float &dw, const b2048_replay_t &rp, int has_replay,
                                                 int8_t *__restrict__ trace_dir, float *__restrict__ trace_value,
                                                 float *__restrict__ trace_dw, uint16_t *__restrict__ trace_spawn,
-                                                int64_t trace_len, StepCounters &c, const MovePrep<N> *prep = nullptr)
+                                                int64_t trace_len, StepCounters &c, const MovePrep<N> *prep = nullptr,
+                                                Publish publish = Publish())
 {
     constexpr int F = num_feat(N);
     uint64_t board = s.board;
@@ -1046,13 +1053,19 @@ __device__ __forceinline__ bool phase_a_compute(const float *__restrict__ w, con
     else best_move<N, COHERENT>(w, L, board, d, run && !over, ba, bg, bv, bd, bf, nv);
     dw = NAN;
     ub = 0;
+    const bool finished = run && (over || (bf & 2u));
+    if (run && (flags & B2048_F_HAVE_STATE)) {
+        float x = -old_label;                                        // terminal update, r_learning.py:248-249
+        if (!finished) {                                             // :238-241
+            x = __fadd_rn(float(bg), bv);                            // (best_score - score) + best_value
+            x = __fsub_rn(x, old_label);
+        }
+        dw = __fdiv_rn(__fmul_rn(x, alpha), float(F));
+        ub = state;
+    }
+    publish(ub, dw);
     if (run) {
-        const bool finished = over || (bf & 2u);
         if (finished) {
-            if (flags & B2048_F_HAVE_STATE) {                        // r_learning.py:248-249
-                dw = __fdiv_rn(__fmul_rn(-old_label, alpha), float(F));
-                ub = state;
-            }
             if (d == 0) {
                 c.fin++; c.score += score; c.msum += odo;
                 if (!over) c.ovf++;
@@ -1073,12 +1086,6 @@ __device__ __forceinline__ bool phase_a_compute(const float *__restrict__ w, con
                 score = 0; odo = 0; state = 0; old_label = 0.0f; flags = 0;
             }
         } else {
-            if (flags & B2048_F_HAVE_STATE) {                        // :238-241
-                float x = __fadd_rn(float(bg), bv);                  // (best_score - score) + best_value
-                x = __fsub_rn(x, old_label);
-                dw = __fdiv_rn(__fmul_rn(x, alpha), float(F));
-                ub = state;
-            }
             if (d == 0) {
                 c.moves++; c.evals += nv;
                 if (trace_dir && int64_t(odo) < trace_len) {
@@ -1369,18 +1376,26 @@ td_persist_kernel(PersistBuffers pb, PersistCtrl *ctrl, const uint32_t *__restri
         if (tl) tl[0] = clock64();
         // ---- phase A: 4 lanes per slot, 8 slots per warp
         if (FAST) {
-            if (a_warp) {
-                uint64_t ub;
-                float dw;
-                st_dirty |= phase_a_compute<N, true>(pb.w, L, g, alpha, slot0 + a_slot, a_dir, a_in, st, ub, dw, no_replay, 0,
-                                                     nullptr, nullptr, nullptr, nullptr, 0, c, PREP ? &prep : nullptr);
-                if (a_in) {                                   // lane d stages images d and 4 + d (d4_image order)
+            // lane d stages images d and 4 + d (d4_image order).  Except in the DIRECT mode the hand-over to phase B
+            // (the CTA barrier) happens inside phase A, before the spawn and the bookkeeping of the move: the other
+            // 12 warps start on the keys while these 4 finish the step.
+            auto stage = [&](uint64_t ub, float dw) {
+                if (a_in) {
                     uint64_t im = (a_dir & 1) ? flip_h(ub) : ub;
                     if (a_dir & 2) im = flip_v(im);
                     s_img[a_slot * 8 + a_dir] = im;
                     s_img[a_slot * 8 + 4 + a_dir] = transpose(im);
                     if (a_dir == 0) s_dw[a_slot] = dw;
                 }
+                if (!DIRECT) __syncthreads();
+            };
+            if (a_warp) {
+                uint64_t ub;
+                float dw;
+                st_dirty |= phase_a_compute<N, true>(pb.w, L, g, alpha, slot0 + a_slot, a_dir, a_in, st, ub, dw, no_replay, 0,
+                                                     nullptr, nullptr, nullptr, nullptr, 0, c, PREP ? &prep : nullptr, stage);
+            } else if (!DIRECT) {
+                __syncthreads();
             }
         } else {
             for (int base = warp * 8; base < nslots; base += nwarps * 8) {
@@ -1390,7 +1405,7 @@ td_persist_kernel(PersistBuffers pb, PersistCtrl *ctrl, const uint32_t *__restri
             }
         }
         if (DIRECT) grid_barrier(&ctrl->bar, bar_target);     // every slot has read W_t before anyone adds to it
-        else __syncthreads();
+        else if (!FAST) __syncthreads();
         if (tl) tl[1] = clock64();
         // ---- phase B: one thread per (entry, table); image s: key, duplicate test against the lower images,
         //      atomic -- issued image by image so that the key arithmetic overlaps the atomics in flight

@@ -417,7 +417,8 @@ def test_td_lockstep_deterministic_bit_exact(eng, orc, fx, n, B):
 
 
 @pytest.mark.parametrize("n,B,steps,force_generic", [(4, 64, 200, True), (5, 5000, 60, False), (6, 700, 40, False),
-                                                     (2, 4096, 50, False)])
+                                                     (2, 4096, 50, False), (3, 4096, 40, False),
+                                                     (5, 17000, 30, False)])
 def test_td_persistent_paths_bit_exact(eng, orc, fx, monkeypatch, n, B, steps, force_generic):
     """b2048_td_run's persistent kernel, both slot layouts (FAST: state in registers, one phase-B round; generic:
     rounds over global staging) and the stepwise path all give the oracle's bits in the deterministic modes."""
