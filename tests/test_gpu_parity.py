@@ -416,14 +416,16 @@ def test_td_lockstep_deterministic_bit_exact(eng, orc, fx, n, B):
         assert np.array_equal(ha["tile_hist"], ls.hist)
 
 
-@pytest.mark.parametrize("n,B,steps,force_generic", [(4, 64, 200, True), (5, 5000, 60, False), (6, 700, 40, False),
-                                                     (2, 4096, 50, False), (3, 4096, 40, False),
-                                                     (5, 17000, 30, False)])
-def test_td_persistent_paths_bit_exact(eng, orc, fx, monkeypatch, n, B, steps, force_generic):
-    """b2048_td_run's persistent kernel, both slot layouts (FAST: state in registers, one phase-B round; generic:
-    rounds over global staging) and the stepwise path all give the oracle's bits in the deterministic modes."""
+@pytest.mark.parametrize("n,B,steps,force", [(4, 64, 200, "generic"), (5, 5000, 60, None), (6, 700, 40, None),
+                                             (2, 4096, 50, None), (3, 4096, 40, None), (5, 17000, 30, None),
+                                             (4, 3000, 80, None), (3, 1000, 60, None), (2, 2000, 50, None),
+                                             (4, 8, 300, None)])
+def test_td_persistent_paths_bit_exact(eng, orc, fx, monkeypatch, n, B, steps, force):
+    """b2048_td_run's persistent kernel gives the oracle's bits in the deterministic modes in both slot layouts:
+    one phase-B round per CTA with the state in registers ((6, 700), (4, 3000), (3, 1000), (2, 2000), (4, 8)), and
+    the generic layout (rounds over global staging and key lists: forced, or the larger shapes)."""
     ctx, engine, cabi = eng
-    if force_generic:
+    if force == "generic":
         monkeypatch.setenv("B2048_PERSIST_GENERIC", "1")
     for rule, mode, alpha in ((4, cabi.UPD_DETERMINISTIC | cabi.UPD_MEAN, 0.25),
                               (3, cabi.UPD_DETERMINISTIC | cabi.UPD_SUM, 0.25 / B)):
