@@ -423,6 +423,20 @@ def td_extras(args, ctx, engine, cabi, wd):
     dt = timed(lambda: ctx.sweep(boards, seed=0, out=bufs), 3) / 3
     out["sweep_boards_per_sec"] = m / dt
     out["sweep_GBps_algorithmic"] = m * 89 / dt / 1e9
+    # the same sweep on boards met in games (SURVEY 8d config 5's second set: realistic merge density): snapshots of
+    # 131,072 greedy games every 8 moves, played with the weights trained so far
+    del boards, bufs
+    per = min(131072, m)
+    gh = engine.GameBatch(per, seed=5, ctx=ctx).init()
+    snaps = []
+    for _ in range(max(1, m // per)):
+        engine.greedy_play(ctx, n, wd, gh, chunk=8, max_launches=1)
+        snaps.append(gh.board.clone())
+    boards = torch.cat(snaps)
+    del snaps
+    bufs = ctx.sweep(boards, seed=0)
+    dt = timed(lambda: ctx.sweep(boards, seed=0, out=bufs), 3) / 3
+    out["sweep_game_boards_per_sec"] = boards.numel() / dt
     return out
 
 
