@@ -722,9 +722,10 @@ __device__ __forceinline__ float lf_top(const float *__restrict__ w, const uint3
 }
 
 // The same value for depth >= 2 by a whole warp: the two upper levels of the tree are laid out explicitly -- 16
-// level-1 nodes (tile j, direction d) and up to 256 level-2 afterstates (j, d, j2, d2) -- and the 32 lanes share the
-// level-2 afterstates, each walking the subtree below its items depth-first.  With 16 items of very different
-// size only (lf_top) a third of the lanes were active per instruction.  Arena: per-warp shared memory.
+// level-1 nodes (tile j, direction d) and up to 256 level-2 afterstates (j, d, j2, d2).  The valid ones are compacted
+// with a ballot per 32 items and shared evenly by the 32 lanes, each walking the subtree below its items
+// depth-first.  With 16 items of very different size only (lf_top) a third of the lanes were active per instruction;
+// without the compaction the lanes holding invalid items idled.  Arena: per-warp shared memory.
 struct LfArena {
     uint64_t board[16];      // level-1 afterstates
     uint32_t pos2[16];       // their 4 sampled cells (6-bit shifts)
@@ -732,9 +733,19 @@ struct LfArena {
                              // 12-15 game over after spawn j2
     float value1[16];        // direct values
     float value2[256];       // level-2 values
+    // the valid level-2 afterstates, compacted (item = (j, d, j2, d2) index), so that the lanes share them evenly
+    uint64_t a2[256];
+    uint8_t item[256];
+    // depth 3: the leaves below 8 level-2 afterstates at a time, compacted again before the gathers
+    uint64_t leaf[128];
+    float lval[128];         // value per (item in chunk, j3, d3)
+    uint32_t pos3[8], meta3[8];
+    uint8_t lslot[128];
 };
 
-template <int N>
+// BATCH: at depth 3 lay the third level out as well and run the gathers on compacted leaves (pays when the SMs are
+// full of games: +18 % at 16,384 games; with one warp per scheduler the extra round trips per chunk cost 4-8 %)
+template <int N, bool BATCH>
 __device__ __forceinline__ float lf_top2(const float *__restrict__ w, const uint32_t *__restrict__ lut, uint64_t b, int depth,
                                          uint32_t path, const LfParams &P, int lane, LfArena &A)
 {
@@ -797,23 +808,131 @@ __device__ __forceinline__ float lf_top2(const float *__restrict__ w, const uint
         A.meta[lane] = meta;
     }
     __syncwarp();
-    // ---- level 2: 256 items (j, d, j2, d2) over the 32 lanes
+    // ---- level 2: the valid ones of the 256 items (j, d, j2, d2), compacted with a ballot per 32 items
+    const unsigned lt_mask = (1u << lane) - 1u;
+    int nvalid = 0;
 #pragma unroll 1
     for (int it = lane; it < 256; it += 32) {
         const int l = it >> 4, j2 = (it >> 2) & 3, d2 = it & 3;
         const uint32_t meta = A.meta[l];
-        float v = -INFINITY;
+        bool ok = false;
+        uint64_t a2 = 0;
         if ((meta & 3u) == 2u && j2 < int((meta >> 4) & 7u) && !((meta >> (12 + j2)) & 1u)) {
             const int sh = int((A.pos2[l] >> (6 * j2)) & 63u);
             const uint64_t nb2 = A.board[l] | (uint64_t(1u + ((meta >> (8 + j2)) & 1u)) << sh);
             uint32_t gain, fl;
-            const uint64_t a2 = move_dir(L, nb2, d2, gain, fl);
-            if ((fl & 3u) == 1u) {
-                const uint32_t path2 = (path * 16u + uint32_t(l)) * 16u + 4u * uint32_t(j2) + uint32_t(d2);
-                v = lf_dispatch<N>(w, lut, a2, depth - 2, path2, P);
-            }
+            a2 = move_dir(L, nb2, d2, gain, fl);
+            ok = (fl & 3u) == 1u;
         }
-        A.value2[it] = v;
+        A.value2[it] = -INFINITY;
+        const unsigned m = __ballot_sync(FULL, ok);
+        if (ok) {
+            const int pos = nvalid + __popc(m & lt_mask);
+            A.a2[pos] = a2;
+            A.item[pos] = uint8_t(it);
+        }
+        nvalid += __popc(m);
+    }
+    __syncwarp();
+    if (!BATCH || depth != 3) {
+        // each lane walks the subtrees below its share of the valid afterstates depth-first (depth 2: they are leaves)
+#pragma unroll 1
+        for (int q = lane; q < nvalid; q += 32) {
+            const uint32_t it = A.item[q];
+            const uint32_t path2 = (path * 16u + (it >> 4)) * 16u + (it & 15u);
+            A.value2[it] = lf_dispatch<N>(w, lut, A.a2[q], depth - 2, path2, P);
+        }
+    } else {
+        // depth 3: one more level laid out, 8 afterstates (<= 128 leaves) at a time: (a) lanes 0..7 sample the tiles of
+        // their afterstate, (b) all lanes make the candidate leaves (item, j3, d3) and compact the valid ones, (c) the
+        // gathers run on the compacted leaves, (d) lanes 0..7 back the values up (lf_node<N, 1>'s arithmetic).
+#pragma unroll 1
+        for (int q0 = 0; q0 < nvalid; q0 += 8) {
+            if (lane < 8) {
+                uint32_t meta = 0, pos3 = 0;
+                if (q0 + lane < nvalid) {
+                    const uint64_t a2 = A.a2[q0 + lane];
+                    const uint64_t z2 = zero_nibbles(a2);
+                    const int empty2 = popc64(z2);
+                    if (empty2 >= P.since_empty) {
+                        meta = 1u;                                         // the afterstate itself is the leaf
+                    } else {
+                        const uint32_t it = A.item[q0 + lane];
+                        const uint32_t path2 = (path * 16u + (it >> 4)) * 16u + (it & 15u);
+                        const int num3 = P.width < empty2 ? P.width : empty2;
+                        const Philox4 vp = spawn_words(P.seed, P.id, P.move_no, 2u | (path2 << 8));
+                        const Philox4 vt = spawn_words(P.seed, P.id, P.move_no, 3u | (path2 << 8));
+                        const uint32_t sp[4] = {vp.x, vp.y, vp.z, vp.w}, st[4] = {vt.x, vt.y, vt.z, vt.w};
+                        uint64_t lm = z2;
+                        meta = 2u | (uint32_t(num3) << 4);
+#pragma unroll
+                        for (int q = 0; q < 4; q++)
+                            if (q < num3) {
+                                const int sh = kth_empty_shift(lm, int(umulhi32(sp[q], uint32_t(empty2 - q))));
+                                lm &= ~(1ULL << sh);
+                                const uint32_t four = umulhi32(st[q], 10u) == 0 ? 1u : 0u;
+                                pos3 |= uint32_t(sh) << (6 * q);
+                                meta |= four << (8 + q);
+                                if (game_over(a2 | (uint64_t(1u + four) << sh))) meta |= 1u << (12 + q);
+                            }
+                    }
+                }
+                A.pos3[lane] = pos3;
+                A.meta3[lane] = meta;
+            }
+            __syncwarp();
+            int nleaf = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int slot = lane + 32 * k, ql = slot >> 4, j3 = (slot >> 2) & 3, d3 = slot & 3;
+                const uint32_t meta = A.meta3[ql];
+                bool ok = false;
+                uint64_t a3 = 0;
+                if ((meta & 3u) == 1u) {
+                    ok = (slot & 15) == 0;
+                    a3 = A.a2[q0 + ql];
+                } else if ((meta & 3u) == 2u && j3 < int((meta >> 4) & 7u) && !((meta >> (12 + j3)) & 1u)) {
+                    const int sh = int((A.pos3[ql] >> (6 * j3)) & 63u);
+                    const uint64_t nb3 = A.a2[q0 + ql] | (uint64_t(1u + ((meta >> (8 + j3)) & 1u)) << sh);
+                    uint32_t gain, fl;
+                    a3 = move_dir(L, nb3, d3, gain, fl);
+                    ok = (fl & 3u) == 1u;
+                }
+                A.lval[slot] = -INFINITY;
+                const unsigned m = __ballot_sync(FULL, ok);
+                if (ok) {
+                    const int pos = nleaf + __popc(m & lt_mask);
+                    A.leaf[pos] = a3;
+                    A.lslot[pos] = uint8_t(slot);
+                }
+                nleaf += __popc(m);
+            }
+            __syncwarp();
+#pragma unroll 1
+            for (int p = lane; p < nleaf; p += 32) A.lval[A.lslot[p]] = lf_leaf<N>(w, A.leaf[p], P);
+            __syncwarp();
+            if (lane < 8 && q0 + lane < nvalid) {
+                const uint32_t meta = A.meta3[lane];
+                float v;
+                if ((meta & 3u) == 1u) {
+                    v = A.lval[lane * 16];
+                } else {
+                    const int num3 = int((meta >> 4) & 7u);
+                    float avg = 0.0f;
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+                        if (q < num3) {
+                            float bq = fmaxf(fmaxf(A.lval[lane * 16 + 4 * q], A.lval[lane * 16 + 4 * q + 1]),
+                                             fmaxf(A.lval[lane * 16 + 4 * q + 2], A.lval[lane * 16 + 4 * q + 3]));
+                            if ((meta >> (12 + q)) & 1u) bq = -100.0f;
+                            avg = __fadd_rn(avg, bq > 0.0f ? bq : 0.0f);
+                        }
+                    v = __fdiv_rn(avg, float(num3));
+                }
+                A.value2[A.item[q0 + lane]] = v;
+            }
+            __syncwarp();
+        }
     }
     __syncwarp();
     // ---- back up: level 2 -> level 1 (lanes 0..15), level 1 -> root
@@ -864,7 +983,7 @@ look_forward_kernel(const float *__restrict__ w, const uint32_t *__restrict__ lu
     if (q >= m) return;                                                   // warp-uniform
     const LfParams P{seed, __ldg(game_id + q), __ldg(move_no + q), width, since_empty, nullptr};
     const uint32_t path = 4u + uint32_t(__ldg(root_dir + q) & 3);
-    const float v = depth >= 2 ? lf_top2<N>(w, lut, __ldg(boards + q), depth, path, P, lane, arena[threadIdx.x >> 5])
+    const float v = depth >= 2 ? lf_top2<N, false>(w, lut, __ldg(boards + q), depth, path, P, lane, arena[threadIdx.x >> 5])
                                : lf_top<N>(w, lut, __ldg(boards + q), depth, path, P, lane & 15, 0xFFFFu << (lane & 16));
     if (lane == 0) value[q] = v;
 }
@@ -905,7 +1024,7 @@ expectimax_play_kernel(const float *__restrict__ w, const uint32_t *__restrict__
             for (int rd = 0; rd < 4; rd++) {
                 uint32_t gain, fl;
                 const uint64_t a = move_dir(L, board, rd, gain, fl);
-                v4[rd] = (fl & 3u) == 1u ? lf_top2<N>(w, lut, a, depth, 4u + uint32_t(rd), P, lane, arena[threadIdx.x >> 5])
+                v4[rd] = (fl & 3u) == 1u ? lf_top2<N, MINB != 1>(w, lut, a, depth, 4u + uint32_t(rd), P, lane, arena[threadIdx.x >> 5])
                                          : -INFINITY;
             }
         } else {                                                          // half-warps: root directions (0, 1) then (2, 3)

@@ -528,6 +528,16 @@ def test_look_forward_and_expectimax_play_vs_oracle(eng, orc, fx, n):
         assert c["moves"] == ref["total_moves"] and c["finished"] == num and c["score_sum"] == ref["scores"].sum()
         td = tdir.cpu().numpy()
         assert all((td[j, :h["moves"][j]] >= 0).all() and (td[j, h["moves"][j]:] == -2).all() for j in range(num))
+    # more than 2,048 games: the launcher's high-occupancy variant, which at depth 3 also lays the third level out and
+    # gathers on compacted leaves; 10 moves per game keep the oracle's share short
+    if n == 4:
+        big = 2304
+        ref = orc.play_expectimax(n, w, 32, 7, big, 3, 4, 9, step_limit=10, threads=orc.max_threads())
+        games = engine.GameBatch(big, seed=32, ctx=ctx).init(first_id=7)
+        engine.expectimax_play(ctx, n, wd, games, 3, 4, 9, step_limit=10)
+        h, c = games.to_host(), games.read_counters()
+        assert np.array_equal(h["board"], ref["boards"]) and np.array_equal(h["score"].astype(np.int64), ref["scores"])
+        assert c["moves"] == ref["total_moves"] == 10 * big
     # depth 0 == greedy play
     g0 = engine.GameBatch(num, seed=31, ctx=ctx).init(first_id=100)
     engine.expectimax_play(ctx, n, wd, g0, 0)
