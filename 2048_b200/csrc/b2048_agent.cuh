@@ -739,7 +739,7 @@ struct LfArena {
     // depth 3: the leaves below 8 level-2 afterstates at a time, compacted again before the gathers
     uint64_t leaf[128];
     float lval[128];         // value per (item in chunk, j3, d3)
-    uint32_t pos3[8], meta3[8];
+    uint32_t pos3[32], meta3[32];   // sampled for 32 afterstates at a time (all lanes busy)
     uint8_t lslot[128];
 };
 
@@ -843,21 +843,22 @@ __device__ __forceinline__ float lf_top2(const float *__restrict__ w, const uint
             A.value2[it] = lf_dispatch<N>(w, lut, A.a2[q], depth - 2, path2, P);
         }
     } else {
-        // depth 3: one more level laid out, 8 afterstates (<= 128 leaves) at a time: (a) lanes 0..7 sample the tiles of
-        // their afterstate, (b) all lanes make the candidate leaves (item, j3, d3) and compact the valid ones, (c) the
-        // gathers run on the compacted leaves, (d) lanes 0..7 back the values up (lf_node<N, 1>'s arithmetic).
+        // depth 3: one more level laid out: (a) every lane samples the tiles of one afterstate (32 at a time: the two
+        // Philox calls per node are a third of the instructions of this branch); then 8 afterstates (<= 128 leaves) at
+        // a time: (b) all lanes make the candidate leaves (item, j3, d3) and compact the valid ones, (c) the gathers run
+        // on the compacted leaves, (d) lanes 0..7 back the values up (lf_node<N, 1>'s arithmetic).
 #pragma unroll 1
-        for (int q0 = 0; q0 < nvalid; q0 += 8) {
-            if (lane < 8) {
+        for (int qs = 0; qs < nvalid; qs += 32) {
+            {
                 uint32_t meta = 0, pos3 = 0;
-                if (q0 + lane < nvalid) {
-                    const uint64_t a2 = A.a2[q0 + lane];
+                if (qs + lane < nvalid) {
+                    const uint64_t a2 = A.a2[qs + lane];
                     const uint64_t z2 = zero_nibbles(a2);
                     const int empty2 = popc64(z2);
                     if (empty2 >= P.since_empty) {
                         meta = 1u;                                         // the afterstate itself is the leaf
                     } else {
-                        const uint32_t it = A.item[q0 + lane];
+                        const uint32_t it = A.item[qs + lane];
                         const uint32_t path2 = (path * 16u + (it >> 4)) * 16u + (it & 15u);
                         const int num3 = P.width < empty2 ? P.width : empty2;
                         const Philox4 vp = spawn_words(P.seed, P.id, P.move_no, 2u | (path2 << 8));
@@ -881,18 +882,21 @@ __device__ __forceinline__ float lf_top2(const float *__restrict__ w, const uint
                 A.meta3[lane] = meta;
             }
             __syncwarp();
+#pragma unroll 1
+            for (int q0 = qs; q0 < nvalid && q0 < qs + 32; q0 += 8) {
+            const int m0 = q0 - qs;                                        // first pos3 / meta3 entry of this group of 8
             int nleaf = 0;
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 const int slot = lane + 32 * k, ql = slot >> 4, j3 = (slot >> 2) & 3, d3 = slot & 3;
-                const uint32_t meta = A.meta3[ql];
+                const uint32_t meta = A.meta3[m0 + ql];
                 bool ok = false;
                 uint64_t a3 = 0;
                 if ((meta & 3u) == 1u) {
                     ok = (slot & 15) == 0;
                     a3 = A.a2[q0 + ql];
                 } else if ((meta & 3u) == 2u && j3 < int((meta >> 4) & 7u) && !((meta >> (12 + j3)) & 1u)) {
-                    const int sh = int((A.pos3[ql] >> (6 * j3)) & 63u);
+                    const int sh = int((A.pos3[m0 + ql] >> (6 * j3)) & 63u);
                     const uint64_t nb3 = A.a2[q0 + ql] | (uint64_t(1u + ((meta >> (8 + j3)) & 1u)) << sh);
                     uint32_t gain, fl;
                     a3 = move_dir(L, nb3, d3, gain, fl);
@@ -912,7 +916,7 @@ __device__ __forceinline__ float lf_top2(const float *__restrict__ w, const uint
             for (int p = lane; p < nleaf; p += 32) A.lval[A.lslot[p]] = lf_leaf<N>(w, A.leaf[p], P);
             __syncwarp();
             if (lane < 8 && q0 + lane < nvalid) {
-                const uint32_t meta = A.meta3[lane];
+                const uint32_t meta = A.meta3[m0 + lane];
                 float v;
                 if ((meta & 3u) == 1u) {
                     v = A.lval[lane * 16];
@@ -932,6 +936,7 @@ __device__ __forceinline__ float lf_top2(const float *__restrict__ w, const uint
                 A.value2[A.item[q0 + lane]] = v;
             }
             __syncwarp();
+            }
         }
     }
     __syncwarp();
