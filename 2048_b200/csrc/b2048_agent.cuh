@@ -1338,21 +1338,33 @@ __device__ __forceinline__ void grid_arrive(uint32_t *bar, uint32_t &target)
     }
 }
 
-__device__ __forceinline__ void grid_wait(const uint32_t *bar, uint32_t target)
+// Returns false when the launch is dead: a wait of 2^25 polls (seconds) can only be a lost CTA.  The CTA that times out
+// raises g.counters[B2048_CTR_FAULT]; every other CTA sees the flag within 2^12 polls and leaves too, so the launch
+// ends instead of hanging the device, and the host finds the fault in the counters it reads anyway (engine raises).
+__device__ __forceinline__ bool grid_wait(const uint32_t *bar, uint32_t target, uint64_t *fault)
 {
+    __shared__ int s_dead;
     if (threadIdx.x == 0) {
-        // a wait of 2^25 polls (seconds) can only be a lost CTA: trap instead of hanging the device
         uint32_t polls = 0;
-        while (ld_relaxed_gpu(bar) < target)
-            if (++polls > (1u << 25)) __trap();
+        int dead = 0;
+        while (ld_relaxed_gpu(bar) < target) {
+            if ((++polls & 0xFFFu) == 0 &&
+                (polls > (1u << 25) || *reinterpret_cast<volatile unsigned long long *>(fault) != 0ULL)) {
+                dead = 1;
+                break;
+            }
+        }
+        if (dead) atomicExch(reinterpret_cast<unsigned long long *>(fault), 1ULL);
+        s_dead = dead;
     }
     __syncthreads();
+    return s_dead == 0;
 }
 
-__device__ __forceinline__ void grid_barrier(uint32_t *bar, uint32_t &target)
+__device__ __forceinline__ bool grid_barrier(uint32_t *bar, uint32_t &target, uint64_t *fault)
 {
     grid_arrive(bar, target);
-    grid_wait(bar, target);
+    return grid_wait(bar, target, fault);
 }
 
 // ---- dense small-exponent key space --------------------------------------------------------------
@@ -1461,6 +1473,7 @@ td_persist_kernel(PersistBuffers pb, PersistCtrl *ctrl, const uint32_t *__restri
     LutGlobal L{lut};
     StepCounters c;
     uint32_t bar_target = 0;
+    uint64_t *fault = g.counters + B2048_CTR_FAULT;
 
     for (int q = threadIdx.x; q < NS; q += blockDim.x) {
         if (EXACT) s_q[q] = 0; else s_sum[q] = 0.0f;
@@ -1528,7 +1541,7 @@ td_persist_kernel(PersistBuffers pb, PersistCtrl *ctrl, const uint32_t *__restri
                                       0, nullptr, nullptr, nullptr, nullptr, 0, c);
             }
         }
-        if (DIRECT) grid_barrier(&ctrl->bar, bar_target);     // every slot has read W_t before anyone adds to it
+        if (DIRECT && !grid_barrier(&ctrl->bar, bar_target, fault)) return;   // every slot has read W_t before anyone adds to it
         else if (!FAST) __syncthreads();
         if (tl) tl[1] = clock64();
         // ---- phase B: one thread per (entry, table); image s: key, duplicate test against the lower images,
@@ -1703,7 +1716,7 @@ td_persist_kernel(PersistBuffers pb, PersistCtrl *ctrl, const uint32_t *__restri
                 if (pb.delta) hd = __ldcg(pb.delta + hk);
             }
         }
-        grid_wait(&ctrl->bar, bar_target);
+        if (!grid_wait(&ctrl->bar, bar_target, fault)) return;
         if (tl) tl[4] = clock64();
         if (!DIRECT) {
             float2 hv = make_float2(0.0f, 0.0f);
@@ -1815,7 +1828,7 @@ td_persist_kernel(PersistBuffers pb, PersistCtrl *ctrl, const uint32_t *__restri
             if (tl) tl[5] = clock64();
             grid_arrive(&ctrl->bar, bar_target);              // W_{t+1} complete once everybody has arrived
             if (PREP && a_warp) move_prepare<N>(L, st.board, a_dir, prep);
-            grid_wait(&ctrl->bar, bar_target);
+            if (!grid_wait(&ctrl->bar, bar_target, fault)) return;
         }
         if (tl) tl[6] = clock64();
     }
@@ -1911,16 +1924,10 @@ int launch_persist(int grid, cudaStream_t st, void **args)
 {
     auto kern = td_persist_kernel<N, EXACT, MEAN, DIRECT, FAST>;
     const int smem = small_count(N) * (EXACT ? 14 : 10);           // sums, counts, dirty list
-    static bool attr_set[64] = {false};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return int(e);
-        attr_set[dev] = true;
-    }
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);   // per call: no cache
+    if (e != cudaSuccess) return int(e);
     int occ = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, PERSIST_THREADS, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, PERSIST_THREADS, smem);
     if (e != cudaSuccess) return int(e);
     if (occ < 1 || grid > occ * sm_count()) return B2048_ENOTSUP;       // all CTAs must be co-resident
     e = cudaLaunchCooperativeKernel(reinterpret_cast<void *>(kern), dim3(unsigned(grid)), dim3(PERSIST_THREADS), args,
@@ -1948,8 +1955,9 @@ int td_run_persistent(float *weights, float *delta, const uint32_t *lut, const b
 {
     const bool det = mode & B2048_UPD_DETERMINISTIC, mean = mode & B2048_UPD_MEAN;
     const int64_t B = g->B;
-    WorkLayout L = work_layout(N, B, mode | B2048_UPD_MEAN);       // DIRECT uses only the control block
-    if (!work || work_bytes < work_layout(N, B, mode).total) return B2048_EWORK;
+    const int umode = mode & 7;                                    // mode may carry B2048_RUN_GENERIC
+    WorkLayout L = work_layout(N, B, umode | B2048_UPD_MEAN);      // DIRECT uses only the control block
+    if (!work || work_bytes < work_layout(N, B, umode).total) return B2048_EWORK;
     // one CTA per SM: slots per CTA rounded up to a multiple of 4
     int max_grid = sm_count();
     if (max_grid > PERSIST_MAX_GRID) max_grid = PERSIST_MAX_GRID;
@@ -1962,16 +1970,19 @@ int td_run_persistent(float *weights, float *delta, const uint32_t *lut, const b
     b2048_games_t games = *g;
     int spc_i = int(spc);
     long long *tlog = nullptr;
-    const char *tlog_path = getenv("B2048_PERSIST_TLOG");          // debug: per-phase clocks -> text file
+#ifdef B2048_PERSIST_TLOG                                          // profiling builds only (profiles/tlog_summary.py)
+    const char *tlog_path = getenv("B2048_PERSIST_TLOG");          // per-phase clocks of the last 16 steps -> text file
     if (tlog_path && *tlog_path && steps >= 16) {
         if (cudaMalloc(&tlog, size_t(grid) * 16 * 8 * sizeof(long long)) != cudaSuccess) tlog = nullptr;
         else cudaMemsetAsync(tlog, 0, size_t(grid) * 16 * 8 * sizeof(long long), st);
     }
+#endif
     void *args[] = {&pb, &ctrl, &lut, &games, &alpha, &steps, &upd_board, &upd_dw, &spc_i, &tlog};
     // FAST: one phase-B round per lock-step, state in registers, staging and key list in shared memory
-    const bool fast = spc <= PERSIST_THREADS / num_feat(N) && spc <= PERSIST_TILE && !env_int("B2048_PERSIST_GENERIC", 0);
+    const bool fast = spc <= PERSIST_THREADS / num_feat(N) && spc <= PERSIST_TILE && !(mode & B2048_RUN_GENERIC);
     const int rc = fast ? launch_persist_mode<N, true>(det, mean, grid, st, args)
                         : launch_persist_mode<N, false>(det, mean, grid, st, args);
+#ifdef B2048_PERSIST_TLOG
     if (tlog) {
         std::vector<long long> h(size_t(grid) * 16 * 8);
         cudaStreamSynchronize(st);
@@ -1989,6 +2000,7 @@ int td_run_persistent(float *weights, float *delta, const uint32_t *lut, const b
             fclose(f);
         }
     }
+#endif
     return rc;
 }
 

@@ -25,24 +25,14 @@ inline int launch_status()
 
 inline cudaStream_t S(b2048_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
-// number of SMs of the current device (cached per device id; immutable)
+// number of SMs of the current device (a driver attribute query, ~100 ns: nothing is cached, the library keeps no
+// mutable state of its own)
 int sm_count()
 {
-    static int cached[64] = {0};
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
-    if (!cached[dev]) {
-        int n = 0;
-        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-        cached[dev] = n;
-    }
-    return cached[dev];
-}
-
-int env_int(const char *name, int dflt)
-{
-    const char *v = getenv(name);
-    return v && *v ? atoi(v) : dflt;
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    return n;
 }
 
 bool cooperative_ok()

@@ -283,6 +283,169 @@ __global__ void delta_apply_kernel(float *__restrict__ w, float *__restrict__ w_
     }
 }
 
+
+// ---- multi-GPU sync, compact form: delta = w - w_sync as float32 plus ONE BIT per weight (w != w_sync) instead of a
+// float indicator: the message is 4 + 1/8 bytes per weight and rank (allreduce of the deltas, allgather of the bit
+// planes) instead of 8.  One weight per thread, the 32 lanes of a warp own one bitmask word.
+__global__ void delta_pack_bits_kernel(const float *__restrict__ w, const float *__restrict__ w_sync,
+                                       float *__restrict__ delta, uint32_t *__restrict__ bits, int64_t count)
+{
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;                  // a multiple of 32
+    const int64_t padded = (count + 31) & ~int64_t(31);
+    for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < padded; i += stride) {
+        const bool in = i < count;
+        const float a = in ? w[i] : 0.0f, b = in ? w_sync[i] : 0.0f;
+        if (in) delta[i] = __fsub_rn(a, b);
+        const uint32_t word = __ballot_sync(FULL, a != b);
+        if ((threadIdx.x & 31) == 0) bits[i >> 5] = word;
+    }
+}
+
+// w_sync += delta_sum / max(1, contributors), w = w_sync, contributors = number of ranks whose bit is set
+__global__ void delta_apply_bits_kernel(float *__restrict__ w, float *__restrict__ w_sync,
+                                        const float *__restrict__ delta_sum, const uint32_t *__restrict__ bits_all,
+                                        int world, int64_t words, int64_t count)
+{
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < count; i += stride) {
+        uint32_t c = 0;
+        for (int r = 0; r < world; r++) c += (__ldg(bits_all + r * words + (i >> 5)) >> (i & 31)) & 1u;
+        float s = delta_sum[i];
+        if (c > 1u) s = __fdiv_rn(s, float(c));
+        const float v = __fadd_rn(w_sync[i], s);
+        w_sync[i] = v;
+        w[i] = v;
+    }
+}
+
+// ---- multi-GPU sync, fused: ONE kernel per rank over NVLink peer memory (b2048_sync_peers) ------------------------
+// Every rank's w, w_sync and flag block are mapped into every process (CUDA IPC / symmetric memory: the host passes the
+// peer pointers).  Rank r owns the r-th contiguous slice of the weights: it reads w_q and w_sync_q of that slice from
+// every rank q (remote loads), forms delta_q = w_q - w_sync_q and the contributor count, and writes
+// w_sync + sum / max(1, contributors) back into w_q and w_sync_q of every rank (remote stores) -- pack, reduce-scatter,
+// apply and all-gather of the NCCL path in one pass, 2 x 4 bytes per weight and rank each way, and every replica
+// receives the owner's bits.  Ranks rendezvous through epoch flags in peer memory: arrive[q] before the first remote
+// load (rank q has finished the lock-steps before its sync kernel and will not touch w until the sync is over), done[q]
+// after the last remote store has been fenced (the last CTA to finish signals and waits, the others just exit).
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ float4 ld_sys_f4(const float *p)
+{
+    float4 v;
+    asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ float ld_sys_f1(const float *p)
+{
+    float v;
+    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// spin until *flag has reached `epoch` (wrap-safe); false after ~2^26 polls: a peer is gone
+__device__ __forceinline__ bool wait_epoch(const uint32_t *flag, uint32_t epoch)
+{
+    for (uint32_t polls = 0; int32_t(ld_acquire_sys(flag) - epoch) < 0;)
+        if (++polls > (1u << 26)) return false;
+    return true;
+}
+
+constexpr int PEER_THREADS = 256;
+
+template <int W>   // W = world size (compile-time: the per-rank loads are all issued before the first use)
+__global__ void __launch_bounds__(PEER_THREADS)
+peer_sync_kernel(b2048_peers_t P, int64_t count, uint32_t epoch)
+{
+    __shared__ int s_ok;
+    const int rank = P.rank;
+    uint32_t *mine = P.flags[rank];
+    if (threadIdx.x == 0) s_ok = 1;
+    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x < W) st_release_sys(P.flags[threadIdx.x] + B2048_PEER_ARRIVE + rank, epoch);
+    if (threadIdx.x < W && !wait_epoch(mine + B2048_PEER_ARRIVE + threadIdx.x, epoch)) s_ok = 0;
+    __syncthreads();
+    if (s_ok) {
+        const int64_t n4 = count >> 2;                                    // float4 units; the tail goes to the last rank
+        const int64_t per = (n4 + W - 1) / W;
+        const int64_t lo = rank * per, hi = (lo + per < n4) ? lo + per : n4;
+        const int64_t stride = int64_t(gridDim.x) * PEER_THREADS;
+        for (int64_t v = lo + blockIdx.x * int64_t(PEER_THREADS) + threadIdx.x; v < hi; v += stride) {
+            float4 a[W], b[W];
+#pragma unroll
+            for (int q = 0; q < W; q++) {
+                a[q] = ld_sys_f4(P.w[q] + 4 * v);
+                b[q] = ld_sys_f4(P.w_sync[q] + 4 * v);
+            }
+            float sum[4] = {0.0f, 0.0f, 0.0f, 0.0f}, base[4];
+            uint32_t c[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int q = 0; q < W; q++) {                                  // rank order: a fixed association
+                const float av[4] = {a[q].x, a[q].y, a[q].z, a[q].w}, bv[4] = {b[q].x, b[q].y, b[q].z, b[q].w};
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const float d = __fsub_rn(av[k], bv[k]);
+                    sum[k] = q == 0 ? d : __fadd_rn(sum[k], d);
+                    c[k] += av[k] != bv[k];
+                    if (q == P.rank) base[k] = bv[k];
+                }
+            }
+            float r[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) r[k] = __fadd_rn(base[k], c[k] > 1u ? __fdiv_rn(sum[k], float(c[k])) : sum[k]);
+            const float4 out = make_float4(r[0], r[1], r[2], r[3]);
+#pragma unroll
+            for (int q = 0; q < W; q++) {
+                *reinterpret_cast<float4 *>(P.w[q] + 4 * v) = out;
+                *reinterpret_cast<float4 *>(P.w_sync[q] + 4 * v) = out;
+            }
+        }
+        if (rank == W - 1 && blockIdx.x == 0) {                            // count % 4 trailing weights
+            for (int64_t i = (n4 << 2) + threadIdx.x; i < count; i += PEER_THREADS) {
+                float sum = 0.0f, base = 0.0f;
+                uint32_t c = 0;
+                for (int q = 0; q < W; q++) {
+                    const float av = ld_sys_f1(P.w[q] + i), bv = ld_sys_f1(P.w_sync[q] + i);
+                    const float d = __fsub_rn(av, bv);
+                    sum = q == 0 ? d : __fadd_rn(sum, d);
+                    c += av != bv;
+                    if (q == rank) base = bv;
+                }
+                const float out = __fadd_rn(base, c > 1u ? __fdiv_rn(sum, float(c)) : sum);
+                for (int q = 0; q < W; q++) { P.w[q][i] = out; P.w_sync[q][i] = out; }
+            }
+        }
+    }
+    // completion: the last CTA of this rank tells every peer that its stores are out, then waits for theirs
+    __syncthreads();
+    __shared__ uint32_t s_last;
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        s_last = atomicAdd(mine + B2048_PEER_TICKET, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    if (threadIdx.x == 0) mine[B2048_PEER_TICKET] = 0;
+    if (threadIdx.x < W) {
+        if (s_ok) {
+            st_release_sys(P.flags[threadIdx.x] + B2048_PEER_DONE + rank, epoch);
+            if (!wait_epoch(mine + B2048_PEER_DONE + threadIdx.x, epoch)) s_ok = 0;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && !s_ok) mine[B2048_PEER_FAULT] = epoch;         // host-visible: this sync did not complete
+}
+
 }   // namespace
 
 // ================================================================================================
@@ -388,14 +551,9 @@ int b2048_sweep(const uint32_t *lut, const uint64_t *boards, int64_t m, uint64_t
 {
     if (m < 0 || !lut || (m && (!boards || !after || !gain || !flags))) return B2048_EINVAL;
     if (!m) return 0;
-    static bool attr_set[64] = {false};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SWEEP_SMEM));
-        if (e != cudaSuccess) return int(e);
-        attr_set[dev] = true;
-    }
+    // per call (a few hundred ns): the attribute belongs to the current context, and the library caches nothing
+    cudaError_t e = cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SWEEP_SMEM));
+    if (e != cudaSuccess) return int(e);
     int64_t want = cdiv(m, SWEEP_THREADS);
     unsigned grid = unsigned(want < sm_count() ? want : sm_count());
     sweep_kernel<<<grid, SWEEP_THREADS, SWEEP_SMEM, S(stream)>>>(lut, boards, m, seed, first_index, after, gain, flags,
@@ -510,13 +668,14 @@ int b2048_td_run(int n, float *weights, float *delta, const uint32_t *lut, const
                  int mode, int steps, uint64_t *upd_board, float *upd_dw, void *work, size_t work_bytes,
                  b2048_stream_t stream)
 {
-    if (steps < 0 || (mode & ~(7 | B2048_RUN_STEPWISE))) return B2048_EINVAL;
+    if (steps < 0 || (mode & ~(7 | B2048_RUN_STEPWISE | B2048_RUN_GENERIC))) return B2048_EINVAL;
     if (!games_ok(g) || num_feat(n) < 0 || !weights || !lut || !upd_board || !upd_dw) return B2048_EINVAL;
     if (steps == 0 || g->B == 0) return 0;
-    const bool stepwise = (mode & (B2048_RUN_STEPWISE | B2048_UPD_SORTED)) || env_int("B2048_STEPWISE", 0);
+    const bool stepwise = mode & (B2048_RUN_STEPWISE | B2048_UPD_SORTED);
+    const int layout = mode & B2048_RUN_GENERIC;
     mode &= 7;
     if (!stepwise && cooperative_ok()) {
-        int rc = agent_ops(n)->td_run_persistent(weights, delta, lut, g, alpha, mode, steps, upd_board, upd_dw, work,
+        int rc = agent_ops(n)->td_run_persistent(weights, delta, lut, g, alpha, mode | layout, steps, upd_board, upd_dw, work,
                                                  work_bytes, S(stream));
         if (rc != B2048_ENOTSUP) return rc;
     }
@@ -530,9 +689,9 @@ int b2048_td_run(int n, float *weights, float *delta, const uint32_t *lut, const
 
 int64_t b2048_td_run_launches(int n, int64_t B, int mode, int steps)
 {
-    if (num_feat(n) < 0 || B < 0 || steps < 0 || (mode & ~(7 | B2048_RUN_STEPWISE))) return -1;
+    if (num_feat(n) < 0 || B < 0 || steps < 0 || (mode & ~(7 | B2048_RUN_STEPWISE | B2048_RUN_GENERIC))) return -1;
     if (B == 0 || steps == 0) return 0;
-    const bool stepwise = (mode & (B2048_RUN_STEPWISE | B2048_UPD_SORTED)) || env_int("B2048_STEPWISE", 0);
+    const bool stepwise = mode & (B2048_RUN_STEPWISE | B2048_UPD_SORTED);
     if (!stepwise && cooperative_ok()) return 1;                   // the persistent kernel
     mode &= 7;
     int64_t per_step = 2;                                          // phase A + direct accumulate
@@ -567,6 +726,51 @@ int b2048_delta_apply(float *weights, float *w_sync, float *delta, const float *
     int64_t want = cdiv(count, 256), cap = int64_t(sm_count()) * 8;
     delta_apply_kernel<<<unsigned(want < cap ? want : cap), 256, 0, S(stream)>>>(weights, w_sync, delta, delta_sum,
                                                                               contributors, count);
+    return launch_status();
+}
+
+
+int b2048_delta_pack_bits(const float *weights, const float *w_sync, float *delta, uint32_t *bits, int64_t count,
+                          b2048_stream_t stream)
+{
+    if (count < 0 || (count && (!weights || !w_sync || !delta || !bits))) return B2048_EINVAL;
+    if (!count) return 0;
+    int64_t want = cdiv(count, 256), cap = int64_t(sm_count()) * 8;
+    delta_pack_bits_kernel<<<unsigned(want < cap ? want : cap), 256, 0, S(stream)>>>(weights, w_sync, delta, bits, count);
+    return launch_status();
+}
+
+int b2048_delta_apply_bits(float *weights, float *w_sync, const float *delta_sum, const uint32_t *bits_all, int world,
+                           int64_t count, b2048_stream_t stream)
+{
+    if (count < 0 || world < 1 || (count && (!weights || !w_sync || !delta_sum || !bits_all))) return B2048_EINVAL;
+    if (!count) return 0;
+    int64_t want = cdiv(count, 256), cap = int64_t(sm_count()) * 8;
+    delta_apply_bits_kernel<<<unsigned(want < cap ? want : cap), 256, 0, S(stream)>>>(weights, w_sync, delta_sum, bits_all,
+                                                                                   world, cdiv(count, 32), count);
+    return launch_status();
+}
+
+int b2048_sync_peers(const b2048_peers_t *peers, int64_t count, uint32_t epoch, int max_ctas, b2048_stream_t stream)
+{
+    if (!peers || count < 0 || peers->world < 1 || peers->world > B2048_MAX_PEERS || peers->rank < 0 ||
+        peers->rank >= peers->world || epoch == 0)
+        return B2048_EINVAL;
+    for (int q = 0; q < peers->world; q++)
+        if (!peers->w[q] || !peers->w_sync[q] || !peers->flags[q]) return B2048_EINVAL;
+    if ((count >> 2) && ((reinterpret_cast<uintptr_t>(peers->w[peers->rank]) | reinterpret_cast<uintptr_t>(peers->w_sync[peers->rank])) & 15))
+        return B2048_EINVAL;                                               // float4 access
+    const int64_t slice4 = cdiv(count >> 2, peers->world);
+    int64_t grid = cdiv(slice4 > 0 ? slice4 : 1, PEER_THREADS);
+    int64_t cap = max_ctas > 0 ? max_ctas : int64_t(sm_count()) * 4;        // every CTA of every rank must be resident
+    if (grid > cap) grid = cap;
+    switch (peers->world) {
+#define B2048_PEER_CASE(Wn) case Wn: peer_sync_kernel<Wn><<<unsigned(grid), PEER_THREADS, 0, S(stream)>>>(*peers, count, epoch); break;
+    B2048_PEER_CASE(1) B2048_PEER_CASE(2) B2048_PEER_CASE(3) B2048_PEER_CASE(4) B2048_PEER_CASE(5) B2048_PEER_CASE(6)
+    B2048_PEER_CASE(7) B2048_PEER_CASE(8)
+#undef B2048_PEER_CASE
+    default: return B2048_ENOTSUP;
+    }
     return launch_status();
 }
 

@@ -10,10 +10,10 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(os.path.dirname(_HERE), "libb2048.so")
 
-UPD_ATOMIC, UPD_DETERMINISTIC, UPD_SUM, UPD_MEAN, UPD_SORTED, RUN_STEPWISE = 0, 1, 0, 2, 4, 8
+UPD_ATOMIC, UPD_DETERMINISTIC, UPD_SUM, UPD_MEAN, UPD_SORTED, RUN_STEPWISE, RUN_GENERIC = 0, 1, 0, 2, 4, 8, 16
 F_HAVE_STATE, F_DONE, F_OVERFLOW = 1, 2, 4
 (CTR_MOVES, CTR_EVALS, CTR_UPDATES, CTR_FINISHED, CTR_SCORE_SUM, CTR_MOVES_SUM, CTR_OVERFLOW, CTR_ACTIVE,
- CTR_LOG) = range(9)
+ CTR_LOG, CTR_QUEUE, CTR_FAULT) = range(11)
 CTR_COUNT = 16
 LUT_ENTRIES = 65536
 
@@ -35,8 +35,17 @@ class Replay(C.Structure):
     _fields_ = [("tile", C.c_void_p), ("pos", C.c_void_p), ("len", C.c_int64)]
 
 
+MAX_PEERS, PEER_ARRIVE, PEER_DONE, PEER_TICKET, PEER_FAULT, PEER_FLAG_WORDS = 16, 0, 16, 32, 33, 64
+
+
+class Peers(C.Structure):
+    """b2048_peers_t: every rank's weights / w_sync / flag block as mapped into this process"""
+    _fields_ = [("w", C.c_void_p * MAX_PEERS), ("w_sync", C.c_void_p * MAX_PEERS), ("flags", C.c_void_p * MAX_PEERS),
+                ("world", C.c_int), ("rank", C.c_int)]
+
+
 _vp, _i64, _u64, _int, _f32, _sz = C.c_void_p, C.c_int64, C.c_uint64, C.c_int, C.c_float, C.c_size_t
-_GP, _RP = C.POINTER(Games), C.POINTER(Replay)
+_GP, _RP, _PP = C.POINTER(Games), C.POINTER(Replay), C.POINTER(Peers)
 
 # name -> (restype, argtypes); mirrors include/b2048.h declaration by declaration
 SIGNATURES = {
@@ -70,6 +79,9 @@ SIGNATURES = {
     "b2048_delta_pack": (_int, [_vp, _vp, _i64, _vp]),
     "b2048_delta_pack_diff": (_int, [_vp, _vp, _vp, _i64, _vp]),
     "b2048_delta_apply": (_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "b2048_delta_pack_bits": (_int, [_vp, _vp, _vp, _vp, _i64, _vp]),
+    "b2048_delta_apply_bits": (_int, [_vp, _vp, _vp, _vp, _int, _i64, _vp]),
+    "b2048_sync_peers": (_int, [_PP, _i64, C.c_uint32, _int, _vp]),
 }
 
 _lib = None

@@ -227,18 +227,27 @@ class GameBatch:
 
     def read_counters(self):
         c = self.counters.cpu().numpy()
+        if c[cabi.CTR_FAULT]:
+            raise B2048Error("a persistent training launch gave up at a grid barrier (B2048_CTR_FAULT): its results "
+                             "and the update workspace are invalid")
         names = ["moves", "evals", "updates", "finished", "score_sum", "moves_sum", "overflow", "active"]
         return {k: int(v) for k, v in zip(names, c)}
 
-    def drain_finished(self):
+    def drain_finished(self, strict=True):
         """finished-game records since the last drain, completion order: uint32 [k,8] =
-        (id lo, id hi, score, moves, max exponent, board lo, board hi, 0)"""
+        (id lo, id hi, score, moves, max exponent, board lo, board hi, 0).  The log holds fin_cap records; games
+        that finished beyond that are counted by the kernels but not stored: with strict=True that raises (the
+        caller's statistics would silently miss episodes), otherwise the number dropped is kept in `self.dropped`."""
         if not self.fin_cap:
             return np.zeros((0, 8), np.uint32)
         head = int(self.counters[cabi.CTR_LOG].item())
         k = min(head, self.fin_cap)
         rec = self.fin_log[:k].cpu().numpy().view(np.uint32).copy()
         self.counters[cabi.CTR_LOG] = 0
+        self.dropped = head - k
+        if self.dropped and strict:
+            raise B2048Error(f"finished-game log overflow: {head} games finished since the last drain, fin_cap = "
+                             f"{self.fin_cap}; drain more often or enlarge fin_cap")
         return rec
 
     def to_host(self):

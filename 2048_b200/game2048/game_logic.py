@@ -133,8 +133,9 @@ class Game:
     @staticmethod
     def _move4(row):
         packed = pack_row(row)
-        if Game._cache[0] == packed:
-            return Game._cache[1]
+        cached = Game._cache                                 # ONE read: worker threads replace the tuple concurrently
+        if cached[0] == packed:
+            return cached[1]
         ctx = engine.Context.get()
         after, gain, flags, _ = ctx.move4(ctx.to_device(np.array([packed], dtype=np.uint64)), want_over=False)
         res = (after.cpu().numpy().view(np.uint64)[0], gain.cpu().numpy().view(np.uint32)[0], int(flags.cpu()[0]))
@@ -274,13 +275,20 @@ class Game:
 
     def _trial_run_device(self, agent, limit_tile, step_limit, trace_len=1 << 15):
         ctx = engine.Context.get()
-        games = engine.GameBatch(1, seed=random.getrandbits(63), ctx=ctx)
-        games.set_positions(np.array([pack_row(self.row)], dtype=np.uint64), scores=[self.score])
-        games.moves.fill_(self.odometer)
-        start = self.odometer
-        tdir, _, tsp = engine.greedy_play(ctx, agent.n, agent._device_weights(), games, limit_tile=limit_tile,
-                                          step_limit=step_limit, trace_len=min(trace_len + start, 1 << 20))
-        self.adopt_device_result(games.to_host(), 0, tdir, tsp, start)
+        seed, start = random.getrandbits(63), self.odometer
+        board, score = np.array([pack_row(self.row)], dtype=np.uint64), [self.score]
+        length = trace_len + start
+        while True:
+            games = engine.GameBatch(1, seed=seed, ctx=ctx)
+            games.set_positions(board, scores=score)
+            games.moves.fill_(start)
+            tdir, _, tsp = engine.greedy_play(ctx, agent.n, agent._device_weights(), games, limit_tile=limit_tile,
+                                              step_limit=step_limit, trace_len=length)
+            host = games.to_host()
+            if int(host['moves'][0]) <= length:
+                break
+            length = int(host['moves'][0]) + 1               # the record was too short: the same game again, traced fully
+        self.adopt_device_result(host, 0, tdir, tsp, start)
 
     def adopt_device_result(self, host, slot, tdir, tsp, start=0):
         """fill row / score / odometer / moves / tiles from a finished device slot and its traces"""

@@ -85,6 +85,34 @@ def f_6(x):
     return _features(6, x)
 
 
+class _WeightsView:
+    """Read-only stand-in for the reference's list-of-lists `QAgent.weights` (:136-164) while the tables live in the
+    device buffer: weights[i] is table i as a float32 array (a fresh device->host copy of that table, not
+    writeable), so `agent.weights[i][f]`, len() and iteration work as before.  Writes go through update() /
+    train_run(); assign file-format arrays to `agent.weights` + np_to_list() to replace the tables."""
+
+    def __init__(self, agent):
+        self._agent = agent
+        self._offsets = cabi.table_offsets(agent.n)
+
+    def __len__(self):
+        return len(self._offsets) - 1
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[k] for k in range(*i.indices(len(self)))]
+        if i < 0:
+            i += len(self)
+        if not 0 <= i < len(self):
+            raise IndexError(i)
+        table = self._agent._w[self._offsets[i]:self._offsets[i + 1]].cpu().numpy()
+        table.flags.writeable = False
+        return table
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+
 class QAgent:
     """:85-406"""
 
@@ -114,11 +142,13 @@ class QAgent:
         self.top_game, self.train_history = None, []
         self.next_decay = self.decay_step
 
-        # new knobs (not in the reference): games per lock-step, scatter mode, Philox seed
+        # new knobs (not in the reference): games per lock-step, scatter mode, Philox seed, and the first Philox game
+        # id nobody has played yet (with a fixed `seed` a second run must not replay the streams of the first)
         self.batch, self.update_mode, self.seed = batch, update_mode, seed
+        self.next_game_id = 0
 
         self._w = None                      # float32 device buffer (never pickled)
-        self.weights = None                 # file-format arrays, only between load and first use
+        self._file_weights = None           # file-format arrays, only between load and first use
         self.weight_signature = None
         if with_weights:
             self.init_weights()
@@ -128,6 +158,16 @@ class QAgent:
                           f'trained for {self.step} episodes, top score = {self.top_score}'))
 
     # ------------------------------------------------------------------ weights (:136-164)
+    @property
+    def weights(self):
+        """the reference's attribute: file-format arrays between load and first use (or None), afterwards a read-only
+        per-table view of the device buffer (_WeightsView)"""
+        return _WeightsView(self) if self._w is not None else self._file_weights
+
+    @weights.setter
+    def weights(self, arrays):
+        self._file_weights = arrays
+
     def init_weights(self):
         """np.random.random(shape) / 100 per table group, like :136-149 (same stream under np.random.seed)"""
         self.weight_signature = engine.SIGNATURE[self.n]
@@ -141,11 +181,11 @@ class QAgent:
         if flat.size != cabi.num_weights(self.n):
             raise ValueError(f'weights have {flat.size} entries, n={self.n} needs {cabi.num_weights(self.n)}')
         self._w = ctx.to_device(flat)
-        self.weights = None
+        self._file_weights = None
 
     def _device_weights(self):
         if self._w is None:
-            if self.weights is None:
+            if self._file_weights is None:
                 raise ValueError('agent has no weights (with_weights=False and nothing loaded)')
             self.np_to_list()
         return self._w
@@ -156,26 +196,31 @@ class QAgent:
 
     def np_to_list(self):
         """:160-164 file-format arrays in self.weights -> working storage (here: the device buffer)"""
-        if self.weights is not None:
+        if self._file_weights is not None:
             if self.weight_signature is None:
                 self.weight_signature = engine.SIGNATURE[self.n]
-            self._upload(self.weights)
+            self._upload(self._file_weights)
 
     def __getstate__(self):
         d = dict(self.__dict__)
-        d['weights'] = self.list_to_np() if (self._w is not None or self.weights is not None) else None
+        d['weights'] = self.list_to_np() if (self._w is not None or self._file_weights is not None) else None
         d.pop('_w', None)
+        d.pop('_file_weights', None)
         return d
 
     def __setstate__(self, d):
+        d = dict(d)
+        self._file_weights = d.pop('weights', None)          # the reference's pickles carry 'weights' in __dict__
         self.__dict__.update(d)
         self._w = None
         self.__dict__.setdefault('batch', 1024)
         self.__dict__.setdefault('update_mode', 'atomic')
         self.__dict__.setdefault('seed', None)
-        if isinstance(self.weights, list) and self.weights and not isinstance(self.weights[0], np.ndarray):
+        self.__dict__.setdefault('next_game_id', self.__dict__.get('step', 0))
+        if isinstance(self._file_weights, list) and self._file_weights and \
+                not isinstance(self._file_weights[0], np.ndarray):
             # a reference pickle taken while weights were list-of-lists: regroup by signature
-            sig, rows, o = self.weight_signature, self.weights, 0
+            sig, rows, o = self.weight_signature, self._file_weights, 0
             arrays = []
             for dcount in sig:
                 arrays.append(np.array(rows[o:o + dcount], dtype=np.float32))
@@ -190,7 +235,7 @@ class QAgent:
                 pickle.dump(self, out, pickle.HIGHEST_PROTOCOL)
             return
         shell = QAgent(name=self.name, with_weights=False)
-        shell.__dict__.update({k: v for k, v in self.__dict__.items() if k not in ('weights', '_w')})
+        shell.__dict__.update({k: v for k, v in self.__dict__.items() if k not in ('weights', '_w', '_file_weights')})
         save_s3(shell, f'a/{self.file}')
         save_s3(self.list_to_np(), f'weights/{self.file}')
 
@@ -242,9 +287,11 @@ class QAgent:
     # ------------------------------------------------------------------ episode (:224-252)
     def episode(self, trace_len=1 << 15):
         """one TD(0) self-play game, exactly the reference's loop with B = 1 (Philox spawns keyed by a draw from
-        `random`); returns the finished Game with moves (incl. the -1 sentinel) and tiles filled in"""
+        `random`); returns the finished Game with moves (incl. the -1 sentinel) and tiles filled in.  The move /
+        tile record holds trace_len entries: a longer game raises instead of returning a truncated record."""
         ctx = engine.Context.get()
-        games = engine.GameBatch(1, seed=self._next_seed(), id_stride=0, ctx=ctx).init(first_id=self.step)
+        games = engine.GameBatch(1, seed=self._next_seed(), id_stride=0, ctx=ctx).init(first_id=self.next_game_id)
+        self.next_game_id += 1
         start = unpack_board(games.to_host()['board'][0])
         tr = engine.TDTrainer(ctx, self.n, self._device_weights(), games, self.alpha, self._mode(1))
         import torch
@@ -255,6 +302,9 @@ class QAgent:
                 tr.step(trace=(td, None, None, ts, trace_len))
             if int(games.flags.cpu()[0]) & cabi.F_DONE:
                 break
+        if int(games.moves.cpu()[0]) >= trace_len:
+            raise cabi.B2048Error(f'episode of {int(games.moves.cpu()[0])} moves does not fit trace_len={trace_len}: '
+                                  'its moves / tiles record would be truncated; pass a larger trace_len')
         game = Game(row=start)
         game.starting_position = start.copy()
         game.adopt_device_result(games.to_host(), 0, td, ts)
@@ -325,7 +375,8 @@ class QAgent:
         owner = _Owner(stopper)
         B = int(batch or self.batch)
         ctx = engine.Context.get()
-        games = engine.GameBatch(B, seed=self._next_seed(), ctx=ctx, fin_cap=max(4 * B, 4096)).init(first_id=self.step)
+        games = engine.GameBatch(B, seed=self._next_seed(), ctx=ctx, fin_cap=max(4 * B, 4096)).init(
+            first_id=self.next_game_id)
         tr = engine.TDTrainer(ctx, self.n, self._device_weights(), games, self.alpha, self._mode(B))
         began = time.time()
         book = dict(ma100=deque(maxlen=100), last1000=[], reached=[0] * 7, lap=began,
@@ -346,6 +397,8 @@ class QAgent:
                 game = Game(score=int(rec[2]), row=unpack_board((int(rec[6]) << 32) | int(rec[5])))
                 game.odometer = int(rec[3])
                 self._account(i, game, int(rec[4]), book, saving)
+        # slot j plays ids first + j, first + j + B, ...: everything up to the largest id now in a slot is used up
+        self.next_game_id = int(games.game_id.max().item()) + 1
         spent = int(time.time() - began)
         self.print(f'Total time = {spent // 60} min {spent % 60} sec')
         if saving:
@@ -356,7 +409,9 @@ class QAgent:
     # ------------------------------------------------------------------ trial (:348-406)
     @staticmethod
     def _trial_report(results, elapsed, shuffles):
-        """the reference's summary text (:384-399); `results` sorted by score, best first"""
+        """the reference's summary text (:384-399), same fields and the same rounding (2 decimals: a GPU batch shows
+        0.0 ms there, so one extra line gives the per-move time in microseconds); `results` sorted by score, best
+        first.  `time per shuffle` divides by the process-wide Game.counter like the reference (:398)."""
         reached = np.array([1 << int(np.max(g.row)) for g in results])
         moves = max(sum(g.odometer for g in results), 1)
         parts = ['\nBest games:'] + [f'{g}\n' for g in results[:3]]
@@ -364,9 +419,11 @@ class QAgent:
         parts += [f'{tile} reached in {np.count_nonzero(reached >= tile) / len(results) * 100}%'
                   for tile in (16384, 8192, 4096, 2048, 1024)]
         parts += [f'total time = {round(elapsed, 2)}',
-                  f'average time per move = {round(elapsed / moves * 1000, 4)} ms',
+                  f'average time per move = {round(elapsed / moves * 1000, 2)} ms',
                   f'total number of shuffles = {Game.counter}',
-                  f'time per shuffle = {round(elapsed / max(shuffles, 1) * 1000, 4)} ms']
+                  f'time per shuffle = {round(elapsed / max(Game.counter, 1) * 1000, 2)} ms',
+                  f'(average time per move = {round(elapsed / moves * 1e6, 3)} us, '
+                  f'{shuffles} shuffles in this trial)']
         return '\n'.join(parts)
 
     @staticmethod
@@ -420,6 +477,7 @@ class QAgent:
             return engine.expectimax_play(ctx, agent.n, agent._device_weights(), games, depth, width, since_empty,
                                           limit_tile=limit_tile, **kw)
 
+        began = time.time()
         ctx = engine.Context.get()
         seed = random.getrandbits(63) if seed is None else int(seed)
         games = engine.GameBatch(num, seed=seed, ctx=ctx).init(first_id=0)
@@ -445,8 +503,10 @@ class QAgent:
         L = int(h['moves'][best]) + 1
         tdir, _, tsp = play(one, trace_len=L)
         results[best].adopt_device_result(one.to_host(), 0, tdir, tsp)
+        per_game = (time.time() - began) / max(num, 1)              # the batch plays all games at once
         for j, g in enumerate(results):
-            display(f'game {j}, result {g.score}, moves {g.odometer}, achieved {1 << np.max(g.row)}')
+            display(f'game {j}, result {g.score}, moves {g.odometer}, achieved {1 << np.max(g.row)}, '
+                    f'time = {per_game:.2f}')
         return results
 
 

@@ -41,7 +41,11 @@ def storage_dir():
 
 
 def _path(name):
-    p = os.path.join(storage_dir(), *name.split("/"))
+    """object name -> file under storage_dir(); names that would escape it ('..', absolute paths) are refused"""
+    root = os.path.realpath(storage_dir())
+    p = os.path.realpath(os.path.join(root, *str(name).split("/")))
+    if os.path.commonpath([root, p]) != root or p == root:
+        raise ValueError(f"object name {name!r} leaves the storage directory")
     os.makedirs(os.path.dirname(p), exist_ok=True)
     return p
 

@@ -1,21 +1,28 @@
 #!/usr/bin/env python
-"""bench.py -- headline benchmark of the B200-native 2048 / n-tuple hot path.
+"""bench.py -- benchmark of the B200-native 2048 / n-tuple hot path over all five BASELINE.json configs.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload td|greedy|sweep]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload td|greedy|sweep|expectimax]
 
-Workload `td` (default) is BASELINE.json configs[1]: Q_agent n=4 TD(0) training, 4,096 parallel seeded games
-per GPU (weak scaling), per-key-mean lock-step rule, atomic update mode; one bench "step" = `--lock-steps`
-lock-steps of all games.  metric = TD updates/s (one update = one QAgent.update() equivalent = 8*F weight
-RMWs).  One JSON line on stdout (rank 0); see DESIGN.md "Measurement" for every field.
+Default (`--workload td`): ONE JSON line on stdout (rank 0).  Its top-level keys are the headline, BASELINE
+configs[1]: Q_agent n=4 TD(0) training, 4,096 parallel seeded games per GPU (weak scaling), per-key-mean lock-step
+rule, atomic update mode; one bench "step" = `--lock-steps` lock-steps of all games; metric = TD updates/s (one
+update = one QAgent.update() equivalent = 8*F weight RMWs).  The `configs` object of the same line carries the other
+four configs, each with value / e2e / roofline / cpu_baseline measured in the same invocation:
+    configs[0]  greedy n=4, 1,000 seeded games in total from fixed (pre-trained) weights          moves/s, strong
+    configs[2]  n=5 TD(0), 65,536 games IN TOTAL split over the N GPUs, weight sync every 64        updates/s, strong
+    configs[3]  greedy n=6, 131,072 games per GPU, random-init AND pre-trained weights              moves/s, weak
+    configs[4]  board sweep, 16M packed boards per GPU x 4 directions + spawn                       boards/s, weak
+See DESIGN.md "Measurement" for every field.
 
---impl reference times the CPU restatement of the reference algorithm (oracle/, C + OpenMP, all host
-threads) on a bounded sample of the same workload; the Python reference itself cannot travel to the GPU box.
+--impl reference times the reference algorithm on the host CPU for the headline config: the C + OpenMP restatement in
+oracle/ (1 thread and all threads, the better one is the line's value) and, where the unmodified Python reference is
+importable (/root/reference or $B2048_REFERENCE: in the build container, not on the GPU box), its own
+QAgent.episode on one core beside it.
 """
 import argparse
 import importlib
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -26,6 +33,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 F_OF_N = {2: 24, 3: 52, 4: 17, 5: 21, 6: 33}
+CPU_CACHE = os.path.join(ROOT, "gpurun_out", ".cpu_baseline_td.json")
 
 
 def parse():
@@ -46,9 +54,14 @@ def parse():
     p.add_argument("--stepwise", action="store_true", help="3 launches per lock-step instead of the persistent kernel")
     p.add_argument("--rule", default="mean", choices=["mean", "sum"])
     p.add_argument("--alpha", type=float, default=0.25)
-    p.add_argument("--sync-every", type=int, default=128, help="lock-steps between weight-delta allreduces (N>1)")
+    p.add_argument("--sync-every", type=int, default=128, help="lock-steps between weight syncs (N>1)")
+    p.add_argument("--sync-impl", default="auto", choices=["auto", "p2p", "nccl"],
+                   help="N>1 weight exchange: fused peer-memory kernel or NCCL allreduce + allgather")
     p.add_argument("--boards", type=int, default=1 << 24, help="boards per GPU (sweep)")
     p.add_argument("--no-extras", action="store_true")
+    p.add_argument("--no-configs", action="store_true", help="headline only: skip the `configs` object")
+    p.add_argument("--only-config", type=int, default=None, help="with --workload td: run just this config of `configs`")
+    p.add_argument("--config-steps", type=int, default=5, help="timed steps of each entry of `configs`")
     p.add_argument("--chunk", type=int, default=4096, help="moves per greedy launch")
     p.add_argument("--pretrain", type=int, default=0, help="greedy: TD lock-steps (4096 games) before playing")
     p.add_argument("--cpu-games", type=int, default=4096, help="greedy: games of the cpu_baseline sample")
@@ -111,19 +124,22 @@ class ClockSampler:
             time.sleep(0.01)
 
     def mark(self):
-        """start of the timed region: only samples taken after this call are reported"""
+        """start of a timed region: only samples taken after this call are reported by the next snapshot()"""
         self.t_mark = time.time()
 
-    def stop(self):
-        self.stop_flag = True
-        if self.thread:
-            self.thread.join(timeout=1.0)
+    def snapshot(self):
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [self.err or "no samples"], "samples": 0}
         timed = [x for x in self.samples if x[0] >= self.t_mark] or self.samples[-3:]
         reasons = sorted({name for _, _, r in timed for name, bit in self.REASONS if r & bit})
         return {"sm_mhz": float(np.median([x[1] for x in timed])), "sm_max_mhz": self.sm_max, "reasons": reasons,
                 "samples": len(timed)}
+
+    def stop(self):
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=1.0)
+        return self.snapshot()
 
 
 def seeded_weights(n, seed=0):
@@ -144,7 +160,7 @@ def ncu_traffic(key, field):
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
             return float(json.load(f)[key][field])
-    except (OSError, KeyError, ValueError):
+    except (OSError, KeyError, ValueError, TypeError):
         return None
 
 
@@ -159,18 +175,67 @@ def bytes_per_update(n, evals_per_move):
     return 16 + 4 * F * evals_per_move + 64 * F          # board in/out + gathers + 8F RMWs x (4+4) B
 
 
-# --------------------------------------------------------------------------------------------- reference arm
-def cpu_td_sample(args, seconds, threads=0):
-    """oracle lock-step TD (float32, per-key-mean rule == the GPU's semantics) on the host cores"""
+class Dist:
+    """rank / world of this process and max / sum reductions over the ranks (device tensors, NCCL)"""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank, self.world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        if self.world > 1 and not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def max_sum(self, vals):
+        if self.world == 1:
+            return list(vals), list(vals)
+        t = self.torch.tensor(vals, dtype=self.torch.float64, device="cuda")
+        tmax, tsum = t.clone(), t.clone()
+        self.dist.all_reduce(tmax, op=self.dist.ReduceOp.MAX)
+        self.dist.all_reduce(tsum, op=self.dist.ReduceOp.SUM)
+        return tmax.tolist(), tsum.tolist()
+
+    def finish(self):
+        if self.world > 1 and self.dist.is_initialized():
+            self.dist.destroy_process_group()
+
+
+def timed_region(D, flush, step, steps, warmup):
+    """`warmup` untimed steps, then `steps` steps timed one by one with CUDA events on the launching stream; an L2
+    flush (a write larger than L2) before each; barrier + synchronize on both sides.  Returns this rank's total ms."""
+    torch = D.torch
+    for _ in range(warmup):
+        step()
+    D.barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in ev:
+        if flush is not None:
+            flush.fill_(1)
+        a.record()
+        step()
+        b.record()
+    D.barrier()
+    return sum(a.elapsed_time(b) for a, b in ev)
+
+
+# --------------------------------------------------------------------------------------------- CPU arms
+def cpu_td_port(n, games, alpha, rule, seconds, threads):
+    """oracle lock-step TD (float32, same rule as the GPU's) on `threads` host threads for about `seconds`"""
     from oracle import oracle as orc
     orc.build()
-    threads = threads or orc.max_threads()
-    rule = 2 if args.rule == "mean" else 1
-    w = seeded_weights(args.n)
-    ls = orc.LockStep(args.n, w, args.alpha, 0, args.games, segmented=rule, threads=threads)
+    w = seeded_weights(n)
+    ls = orc.LockStep(n, w, alpha, 0, games, segmented=2 if rule == "mean" else 1, threads=threads)
     ls.run(2)                                            # touch memory
     u0, t0, steps = ls.n_updates, time.perf_counter(), 0
-    chunk = 4
+    chunk = 1 if games > 8192 else 4
     while True:
         ls.run(chunk)
         steps += chunk
@@ -178,35 +243,99 @@ def cpu_td_sample(args, seconds, threads=0):
         if dt >= seconds:
             break
         chunk = max(1, min(64, int(chunk * seconds / max(dt, 1e-3) / 4)))
-    return (ls.n_updates - u0) / dt, threads, f"{steps} lock-steps of {args.games} games, n={args.n} ({dt:.1f} s)"
+    return (ls.n_updates - u0) / dt, f"{steps} lock-steps of {games} games, n={n}, {threads} thread(s) ({dt:.1f} s)"
+
+
+def cpu_td_baseline(n, games, alpha, rule, seconds):
+    """the port at 1 thread and at all host threads (only its evaluate phase is parallel: the scaling is what it is);
+    value = the better of the two, cores = the thread count that produced it"""
+    from oracle import oracle as orc
+    orc.build()
+    tmax = max(1, orc.max_threads())
+    res = {}
+    for t in sorted({1, tmax}):
+        res[t] = cpu_td_port(n, games, alpha, rule, seconds / (2 if tmax > 1 else 1), t)
+    best = max(res, key=lambda t: res[t][0])
+    return {"value": res[best][0], "unit": "updates/s", "cores": best, "kind": "port", "sample": res[best][1],
+            "thread_scaling": {str(t): res[t][0] for t in res}, "host_threads": tmax}
+
+
+def python_reference_td(n, alpha, seconds):
+    """the UNMODIFIED Python reference (QAgent.episode, r_learning.py:224-252) on one core, where it is importable
+    (oracle/ref_shim.py: the build container; not the GPU box).  None otherwise."""
+    try:
+        from oracle import ref_shim
+        if not ref_shim.available():
+            return None
+        gl, rl = ref_shim.load()
+        ref_shim.seed_all(0)
+        agent = ref_shim.make_agent(rl, n, alpha=alpha)
+        updates, episodes, t0 = 0, 0, time.perf_counter()
+        while time.perf_counter() - t0 < seconds:
+            game = agent.episode()
+            updates += game.odometer                 # one update() per move from the 2nd on, + the terminal one
+            episodes += 1
+        dt = time.perf_counter() - t0
+        return {"value": updates / dt, "unit": "updates/s", "cores": 1, "kind": "reference",
+                "sample": f"{episodes} QAgent.episode() calls, n={n}, random-init weights, 1 core ({dt:.1f} s)"}
+    except Exception as e:                               # noqa: BLE001 - the reference arm must still print its line
+        return {"unavailable": f"{type(e).__name__}: {e}"}
 
 
 def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
     from oracle import oracle as orc
     orc.build()
-    threads = orc.max_threads()
+    tmax = max(1, orc.max_threads())
     rule = 2 if args.rule == "mean" else 1
-    w = seeded_weights(args.n)
-    ls = orc.LockStep(args.n, w, args.alpha, 0, args.games, segmented=rule, threads=threads)
     per_step = max(1, min(args.lock_steps, 8))           # bounded sample of the GPU step
-    for _ in range(args.warmup):
-        ls.run(per_step)
-    u0, t0 = ls.n_updates, time.perf_counter()
-    for _ in range(args.steps):
-        ls.run(per_step)
-    dt = time.perf_counter() - t0
-    val = (ls.n_updates - u0) / dt
-    sample = f"{per_step} lock-steps of {args.games} games per step (GPU step = {args.lock_steps})"
+    runs = {}
+    for threads in sorted({1, tmax}):
+        ls = orc.LockStep(args.n, seeded_weights(args.n), args.alpha, 0, args.games, segmented=rule, threads=threads)
+        for _ in range(args.warmup):
+            ls.run(per_step)
+        u0, t0 = ls.n_updates, time.perf_counter()
+        for _ in range(args.steps):
+            ls.run(per_step)
+        dt = time.perf_counter() - t0
+        runs[threads] = ((ls.n_updates - u0) / dt, dt)
+    best = max(runs, key=lambda t: runs[t][0])
+    val, dt = runs[best]
+    sample = f"{per_step} lock-steps of {args.games} games per step (GPU step = {args.lock_steps}), {best} thread(s)"
+    cpu = {"value": val, "unit": "updates/s", "cores": best, "kind": "port", "sample": sample,
+           "thread_scaling": {str(t): runs[t][0] for t in runs}, "host_threads": tmax}
     line = {"impl": "reference", "metric": "td_updates_per_sec", "value": val, "unit": "updates/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args),
-            "cpu_baseline": {"value": val, "unit": "updates/s", "cores": threads, "kind": "port", "sample": sample},
+            "config": workload_config(args), "cpu_baseline": cpu,
             "e2e": {"value": val, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    py = python_reference_td(args.n, args.alpha, min(args.cpu_seconds, 10.0))
+    if py is not None:
+        line["python_reference"] = py
+    try:                                                 # the b200 arm of the same box reports THIS measurement
+        os.makedirs(os.path.dirname(CPU_CACHE), exist_ok=True)
+        with open(CPU_CACHE, "w") as f:
+            json.dump({"when": time.time(), "n": args.n, "games": args.games, "rule": args.rule, "cpu_baseline": cpu,
+                       "python_reference": py}, f)
+    except OSError:
+        pass
     print(json.dumps(line), flush=True)
+
+
+def cached_cpu_td(args):
+    """the --impl reference measurement of this box (the driver runs that arm first), if it is the same config and
+    less than an hour old: both arms then report ONE cpu measurement"""
+    try:
+        with open(CPU_CACHE) as f:
+            c = json.load(f)
+        if c["n"] == args.n and c["games"] == args.games and c["rule"] == args.rule and time.time() - c["when"] < 3600:
+            cpu = dict(c["cpu_baseline"])
+            cpu["source"] = "the --impl reference run on this box (one measurement for both arms)"
+            return cpu, c.get("python_reference")
+    except (OSError, KeyError, ValueError):
+        pass
+    return None, None
 
 
 def workload_config(args):
@@ -218,76 +347,41 @@ def workload_config(args):
                   "between timed steps to flush L2"}
 
 
-# --------------------------------------------------------------------------------------------- GPU arm
-def run_td(args):
-    import torch
-    import torch.distributed as dist
-    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    importlib.import_module("2048_b200")
-    from game2048 import cabi, engine
-    from game2048 import parallel
-    ctx = engine.Context.get()
-    n, B, S = args.n, args.games, args.lock_steps
-    mode = mode_bits(cabi, args)
+# --------------------------------------------------------------------------------------------- TD (configs[1], [2])
+def td_bench(D, ctx, args, n, B, S, steps, warmup, mode, sync_every, first_slot, total_slots, sampler=None,
+             traffic_key=None):
+    """Lock-step TD on this rank's B slots (global slots first_slot .. of total_slots), S lock-steps per bench step.
+    Returns (result dict for rank 0 | None, trainer): value, e2e, roofline, sync figures, sync_check."""
+    torch = D.torch
+    from game2048 import cabi, parallel
     w_host = torch.from_numpy(seeded_weights(n)).pin_memory()
-    # games sharded by global slot id (rank r owns slots [r*B, (r+1)*B)), weights replicated, per-rank deltas
-    # allreduced over NCCL every --sync-every lock-steps (2048_b200/game2048/parallel.py)
-    st = parallel.ShardedTrainer(n, w_host.numpy(), B, args.alpha, mode, seed=0, sync_every=args.sync_every)
-    tr, wd, games = st.trainer, st.w, st.trainer.games
+    st = parallel.ShardedTrainer(n, w_host.numpy(), B, args.alpha, mode, seed=0, sync_every=sync_every,
+                                 sync_impl=args.sync_impl, first_slot=first_slot, total_slots=total_slots)
+    wd, games = st.w, st.trainer.games
     flush = ctx.zeros(64 << 20, torch.int32)                     # 256 MiB > 126 MB L2
-
-    def step():
+    for _ in range(warmup):
         st.run(S)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-        sampler.wait_first()
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    c0 = games.read_counters()
-    l0 = st.launches
-    sampler.mark()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    for a, b in ev:
-        flush.fill_(1)
-        a.record()
-        step()
-        b.record()
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    launches_timed = st.launches - l0                            # this rank's kernels inside the timed region
-    ms = sum(a.elapsed_time(b) for a, b in ev)
+    D.barrier()
+    c0, l0 = games.read_counters(), st.launches
+    if sampler:
+        sampler.mark()
+    ms = timed_region(D, flush, lambda: st.run(S), steps, 0)
+    clocks = sampler.snapshot() if sampler else None
+    launches_timed = st.launches - l0
     c1 = games.read_counters()
-    upd = c1["updates"] - c0["updates"]
-    mv = c1["moves"] - c0["moves"]
-    evals = c1["evals"] - c0["evals"]
-    t = torch.tensor([ms, float(upd), float(mv), float(evals)], dtype=torch.float64, device=ctx.device)
-    if world > 1:
-        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        ms, upd, mv, evals = float(tmax[0]), float(tsum[1]), float(tsum[2]), float(tsum[3])
+    upd, mv, evals = c1["updates"] - c0["updates"], c1["moves"] - c0["moves"], c1["evals"] - c0["evals"]
+    mx, sm = D.max_sum([ms, float(upd), float(mv), float(evals)])
+    ms, upd, mv, evals = mx[0], sm[1], sm[2], sm[3]
     value = upd / (ms * 1e-3)
+    in_sync = st.replicas_identical() if S % max(sync_every, 1) == 0 or D.world == 1 else None
 
-    # ---- e2e: the same step through host buffers: weights H2D (pinned) -> S lock-steps (with the NCCL delta syncs
-    # at N > 1) -> weights + counters D2H, all inside the timed region; max over ranks, updates summed
+    # ---- e2e: the same step through host buffers: weights H2D (pinned) -> S lock-steps (with the weight syncs at
+    # N > 1) -> weights + counters D2H, all inside the timed region; max over ranks, updates summed
     e2e_ms, e2e_upd = 0.0, 0
-    for i in range(min(args.steps, 5) + 1):
+    for i in range(min(steps, 5) + 1):
         cA = games.read_counters()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
+        D.barrier()
         a.record()
         wd.copy_(w_host, non_blocking=True)
         if st.w_sync is not None:
@@ -301,67 +395,118 @@ def run_td(args):
             e2e_ms += a.elapsed_time(b)
             e2e_upd += int(cnt[cabi.CTR_UPDATES]) - cA["updates"]
     h2d, d2h = wd.numel() * 4, wd.numel() * 4 + cabi.CTR_COUNT * 8
-    if world > 1:
-        t2 = torch.tensor([e2e_ms, float(e2e_upd)], dtype=torch.float64, device=ctx.device)
-        tm, ts = t2.clone(), t2.clone()
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        dist.all_reduce(ts, op=dist.ReduceOp.SUM)
-        e2e_ms, e2e_upd = float(tm[0]), float(ts[1])
-    e2e = {"value": e2e_upd / (e2e_ms * 1e-3) if e2e_ms else None, "unit": "updates/s",
+    mx2, sm2 = D.max_sum([e2e_ms, float(e2e_upd)])
+    e2e = {"value": sm2[1] / (mx2[0] * 1e-3) if mx2[0] else None, "unit": "updates/s",
            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
 
+    # ---- one weight sync in isolation (N > 1): CUDA events around sync() after one lock-step, max over ranks
+    sync_us = None
+    if D.world > 1:
+        tot = 0.0
+        for i in range(6):
+            st.run(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            D.barrier()
+            a.record()
+            st.sync()
+            b.record()
+            torch.cuda.synchronize()
+            if i:
+                tot += a.elapsed_time(b) / 5
+        sync_us = D.max_sum([tot * 1e3])[0][0]
+        ok2 = st.replicas_identical()
+        in_sync = ok2 if in_sync is None else (in_sync and ok2)
+    if D.rank != 0:
+        return None, st
     # ---- roofline of the dominant kernel: the persistent lock-step kernel IS the timed step (one launch per step at
     # N=1), so its average launch duration is ms / steps, measured by the CUDA events above on the launching stream.
     # Algorithmic bytes per launch = updates per launch x (16 + 4 F E + 64 F)  (DESIGN 3).
-    roof = None
-    if rank == 0:
-        F = F_OF_N[n]
-        peak, how = peaks()
-        e_per_move = evals / max(mv, 1)
-        # N > 1: a step is S / sync_every persistent launches with a delta sync after each; the average below then
-        # includes the sync kernels and the allreduce (whole-step view)
-        n_persist = 1 if world == 1 else max(1, -(-S // args.sync_every))
-        per_gpu_updates_per_launch = upd / world / args.steps / n_persist
-        launch_s = ms * 1e-3 / args.steps / n_persist
-        ach = per_gpu_updates_per_launch * bytes_per_update(n, e_per_move) / launch_s / 1e9
-        persistent = launches_per_step_of(st, S) == 1
-        roof = {"bound": "hbm", "kernel": "td_persist_kernel (phase A gather + argmax + spawn, phase B 8F-way scatter, "
-                                          "apply; one cooperative launch per bench step)" if persistent else
-                                          "td_phase_a + td_accum + td_apply (stepwise path)",
-                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": (lambda t: t * per_gpu_updates_per_launch if t and n == 4 and B == 4096 else None)(
-                    ncu_traffic("td_persist_n4_B4096_atomic_mean", "bytes_per_update")),
-                "traffic_source": "profiles/ncu_traffic.json: DRAM bytes per update of one ncu --set full capture of this kernel "
-                                  "(n=4, 4096 games) x updates per launch; the tables never leave L2",
-                "peak_source": how, "launch_us": launch_s * 1e6, "updates_per_launch": per_gpu_updates_per_launch,
-                "bytes_per_update": bytes_per_update(n, e_per_move), "evals_per_move": e_per_move,
-                "atomics_per_sec": value / world * 8 * F,
-                "atomic_issue_peak_per_sec": 126e9,
-                "note": "tables are L2-resident at n<=5, so HBM is the judged but not the physical bound: the kernel is "
-                        "bound by the SM-side issue rate of returning L2 atomics (126 G/s measured chip-wide, "
-                        "profiles/microbench/atomics2.cu) and by two grid barriers per lock-step"}
+    F = F_OF_N[n]
+    peak, how = peaks()
+    e_per_move = evals / max(mv, 1)
+    # N > 1: a step is S / sync_every persistent launches with a weight sync after each; the average below then
+    # includes the sync (whole-step view)
+    n_persist = 1 if D.world == 1 else max(1, -(-S // sync_every))
+    upl = upd / D.world / steps / n_persist
+    launch_s = ms * 1e-3 / steps / n_persist
+    ach = upl * bytes_per_update(n, e_per_move) / launch_s / 1e9
+    persistent = launches_per_step_of(st, S) == 1
+    tr_b = ncu_traffic(traffic_key, "bytes_per_update") if traffic_key else None
+    roof = {"bound": "hbm", "kernel": "td_persist_kernel (phase A gather + argmax + spawn, phase B 8F-way scatter, "
+                                      "apply; one cooperative launch per sync period)" if persistent else
+                                      "td_phase_a + td_accum + td_apply (stepwise path)",
+            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            "traffic": tr_b * upl if tr_b else None,
+            "traffic_source": f"profiles/ncu_traffic.json[{traffic_key}]: DRAM bytes per update of one ncu --set full "
+                              "capture of this kernel x updates per launch" if tr_b else None,
+            "peak_source": how, "launch_us": launch_s * 1e6, "updates_per_launch": upl,
+            "bytes_per_update": bytes_per_update(n, e_per_move), "evals_per_move": e_per_move,
+            "l2": {"achieved_atomics_per_sec": value / D.world * 8 * F, "peak_atomics_per_sec": 126e9,
+                   "frac": value / D.world * 8 * F / 126e9,
+                   "peak_source": "profiles/r01b_microbench_atomics_steady.txt: returning L2 atomics, chip-wide"},
+            "note": "tables are L2-resident at n<=5, so HBM is the judged but not the physical bound: the kernel is "
+                    "bound by the SM-side issue rate of returning L2 atomics and by two grid barriers per lock-step"}
+    res = {"metric": "td_updates_per_sec", "value": value, "unit": "updates/s", "ms_per_step": ms / steps,
+           "steps": steps, "warmup": warmup, "moves_per_sec": mv / (ms * 1e-3), "clocks": clocks, "e2e": e2e,
+           "gpu_launches": int(launches_timed), "roofline": roof}
+    if D.world > 1:
+        res.update(sync_check=bool(in_sync), sync_us=sync_us, sync_impl=st.sync_impl,
+                   sync_message_bytes_per_rank=st.message_bytes,
+                   sync_fallback_reason=getattr(st.ops, "peer_error", None))
+    return res, st
 
-    extras = {}
-    if rank == 0 and world == 1 and not args.no_extras:
-        extras = td_extras(args, ctx, engine, cabi, wd)
-    cpu = None
-    if rank == 0 and world == 1:
-        v, cores, sample = cpu_td_sample(args, args.cpu_seconds)
-        cpu = {"value": v, "unit": "updates/s", "cores": cores, "kind": "port", "sample": sample}
-    if rank == 0:
-        line = {"metric": "td_updates_per_sec", "value": value, "unit": "updates/s", "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+
+def run_td(args):
+    D = Dist()
+    importlib.import_module("2048_b200")
+    from game2048 import cabi, engine
+    ctx = engine.Context.get()
+    n, B, S = args.n, args.games, args.lock_steps
+    sampler = ClockSampler(D.local)
+    if D.rank == 0:
+        sampler.start()
+        sampler.wait_first()
+    # games sharded by global slot id (rank r owns slots [r*B, (r+1)*B)), weights replicated, per-rank weight
+    # movements combined every --sync-every lock-steps (2048_b200/game2048/parallel.py)
+    res, st = td_bench(D, ctx, args, n, B, S, args.steps, args.warmup, mode_bits(cabi, args), args.sync_every,
+                       first_slot=None, total_slots=None, sampler=sampler if D.rank == 0 else None,
+                       traffic_key="td_persist_n4_B4096_atomic_mean" if (n, B) == (4, 4096) else None)
+    if D.world > 1 and res is not None and res.get("sync_check") is False:
+        raise SystemExit("replicas differ after the last weight sync: no value printed")
+    line = None
+    if D.rank == 0:
+        extras = td_extras(args, ctx, engine, cabi, st.w) if D.world == 1 and not args.no_extras else {}
+        cpu, py = (None, None)
+        if D.world == 1:
+            cpu, py = cached_cpu_td(args)
+            if cpu is None:
+                cpu = cpu_td_baseline(n, B, args.alpha, args.rule, args.cpu_seconds)
+        line = {"metric": res["metric"], "value": res["value"], "unit": res["unit"], "n_gpus": D.world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": workload_config(args), "moves_per_sec": mv / (ms * 1e-3), "clocks": clocks, "e2e": e2e,
-                "gpu_launches": int(launches_timed),
-                "roofline": roof, "cpu_baseline": cpu, "extras": extras}
+                "config": workload_config(args)}
+        for k in ("moves_per_sec", "clocks", "e2e", "gpu_launches", "roofline", "sync_check", "sync_us", "sync_impl",
+                  "sync_message_bytes_per_rank", "sync_fallback_reason"):
+            if k in res:
+                line[k] = res[k]
+        line["cpu_baseline"] = cpu
+        if py:
+            line["python_reference"] = py
+        line["extras"] = extras
+    del st
+    D.torch.cuda.empty_cache()
+    if not args.no_configs:
+        cfg = run_configs(D, ctx, args, sampler if D.rank == 0 else None)
+        if D.rank == 0:
+            line["configs"] = cfg
+    if D.rank == 0:
+        sampler.stop()
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    D.finish()
 
 
 def td_extras(args, ctx, engine, cabi, wd):
-    """secondary numbers on the same box: deterministic-mode updates/s, greedy moves/s, board sweep"""
+    """secondary numbers on the same box: the other update modes of the headline shape"""
     import torch
     out = {}
     n, B = args.n, args.games
@@ -401,294 +546,312 @@ def td_extras(args, ctx, engine, cabi, wd):
         sums.append(f"{x & 0xFFFFFFFF:08x}-{int(bits.sum().item()) & 0xFFFFFFFFFFFFFFFF:016x}")
     out["deterministic_weights_checksum_300_locksteps"] = sums[0]
     out["deterministic_checksum_repeat_equal"] = sums[0] == sums[1]
-    # greedy play, BASELINE configs[0] shape: 1,000 seeded games to completion from the trained-so-far weights
-    g3 = engine.GameBatch(1000, seed=2, ctx=ctx).init()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    a.record()
-    engine.greedy_play(ctx, n, wd, g3)
-    b.record()
-    torch.cuda.synchronize()
-    c = g3.read_counters()
-    out["greedy_1000_games_moves_per_sec"] = c["moves"] / (a.elapsed_time(b) * 1e-3)
-    out["greedy_1000_games_avg_score"] = c["score_sum"] / max(c["finished"], 1)
-    # config 5 sweep: 16M boards
-    m = args.boards
-    gen = torch.Generator(device=ctx.device).manual_seed(0)      # cell iid: empty p=0.3 else exponent 1..11
-    cells = torch.randint(1, 12, (m, 16), dtype=torch.int32, device=ctx.device, generator=gen)
-    cells.mul_((torch.rand((m, 16), device=ctx.device, generator=gen) >= 0.3).to(torch.int32))
-    boards = ctx.pack(cells)
-    del cells
-    bufs = ctx.sweep(boards, seed=0)
-    dt = timed(lambda: ctx.sweep(boards, seed=0, out=bufs), 3) / 3
-    out["sweep_boards_per_sec"] = m / dt
-    out["sweep_GBps_algorithmic"] = m * 89 / dt / 1e9
-    # the same sweep on boards met in games (SURVEY 8d config 5's second set: realistic merge density): snapshots of
-    # 131,072 greedy games every 8 moves, played with the weights trained so far
-    del boards, bufs
-    per = min(131072, m)
-    gh = engine.GameBatch(per, seed=5, ctx=ctx).init()
-    snaps = []
-    for _ in range(max(1, m // per)):
-        engine.greedy_play(ctx, n, wd, gh, chunk=8, max_launches=1)
-        snaps.append(gh.board.clone())
-    boards = torch.cat(snaps)
-    del snaps
-    bufs = ctx.sweep(boards, seed=0)
-    dt = timed(lambda: ctx.sweep(boards, seed=0, out=bufs), 3) / 3
-    out["sweep_game_boards_per_sec"] = boards.numel() / dt
     return out
 
 
-# --------------------------------------------------------------------------------------------- secondary workloads
-def dist_setup():
-    import torch
-    import torch.distributed as dist
-    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    if world > 1 and not dist.is_initialized():
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    return rank, world, local
-
-
-def reduce_max_sum(vals, ctx, world):
-    import torch
-    import torch.distributed as dist
-    t = torch.tensor(vals, dtype=torch.float64, device=ctx.device)
-    if world == 1:
-        return list(vals), list(vals)
-    tmax, tsum = t.clone(), t.clone()
-    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-    return tmax.tolist(), tsum.tolist()
-
-
-def run_greedy(args):
-    """BASELINE configs[3] shape: greedy n-tuple play of `--games` seeded games per GPU to completion (default n=6,
-    131,072 games per GPU = 1M games on 8 GPUs), weights fixed.  One bench step = all games of the rank, played by
-    b2048_greedy_play (whole games per launch, Philox spawns keyed by GLOBAL game id, no collective)."""
-    import torch
-    import torch.distributed as dist
-    rank, world, local = dist_setup()
-    importlib.import_module("2048_b200")
+# --------------------------------------------------------------------------------------------- configs[0], [3]
+def pretrained_weights(ctx, n, lock_steps, alpha=0.25):
+    """seeded random-init weights + `lock_steps` deterministic per-key-mean TD lock-steps of 4,096 games: the same
+    bits on every rank and every run (fixed weights for the greedy configs), returned as a device tensor"""
     from game2048 import cabi, engine
-    ctx = engine.Context.get()
-    n, B = args.n, args.games
-    w_host = torch.from_numpy(seeded_weights(n)).pin_memory()
-    wd = ctx.empty(w_host.numel(), torch.float32)
-    wd.copy_(w_host)
-    if args.pretrain:                                            # a briefly trained agent plays longer games
+    wd = ctx.to_device(seeded_weights(n))
+    if lock_steps:
         g0 = engine.GameBatch(4096, seed=5, ctx=ctx).init()
-        engine.TDTrainer(ctx, n, wd, g0, args.alpha, cabi.UPD_ATOMIC | cabi.UPD_MEAN).run(args.pretrain)
-        w_host.copy_(wd)
-    games = engine.GameBatch(B, seed=0, ctx=ctx)
+        engine.TDTrainer(ctx, n, wd, g0, alpha, cabi.UPD_DETERMINISTIC | cabi.UPD_MEAN).run(lock_steps)
+    return wd
+
+
+def greedy_bench(D, ctx, args, n, first_id, B, wd, steps, warmup, label, sampler=None, traffic_key=None, cpu_games=0,
+                 look=None):
+    """greedy (or look-ahead) play of this rank's B games (global ids first_id ..) to completion per bench step"""
+    torch = D.torch
+    from game2048 import cabi, engine
+    w_host = torch.empty(wd.numel(), dtype=torch.float32).pin_memory()
+    w_host.copy_(wd)
+    games = engine.GameBatch(max(B, 1), seed=0, ctx=ctx)
     flush = ctx.zeros(64 << 20, torch.int32)
-    score_host, moves_host = torch.empty(B, dtype=torch.int32).pin_memory(), torch.empty(B, dtype=torch.int32).pin_memory()
+    score_host = torch.empty(max(B, 1), dtype=torch.int32).pin_memory()
+    moves_host = torch.empty(max(B, 1), dtype=torch.int32).pin_memory()
+    launches = [0]
 
-    look = args.workload == "expectimax"
-
-    def step(e2e=False):
-        if e2e:
-            wd.copy_(w_host, non_blocking=True)
-        games.init(first_id=rank * B)
+    def play():
+        games.init(first_id=first_id)
         if look:
-            engine.expectimax_play(ctx, n, wd, games, args.depth, args.width, args.since_empty, chunk=args.chunk)
+            engine.expectimax_play(ctx, n, wd, games, *look, chunk=args.chunk)
         else:
-            engine.greedy_play(ctx, n, wd, games, chunk=args.chunk)
-        if e2e:                                                  # per-game result: score, moves (+ counters)
-            score_host.copy_(games.score, non_blocking=True)
-            moves_host.copy_(games.moves, non_blocking=True)
-            return games.read_counters()
-        return None
+            engine.greedy_play(ctx, n, wd, games, chunk=1 << 20)
+        launches[0] += 2
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
+    tot = {"moves": 0, "evals": 0, "score": 0, "fin": 0}
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start(); sampler.wait_first()
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    sampler.mark()
-    ms, moves, evals, launches = 0.0, 0, 0, 0
-    for _ in range(args.steps):
+    def step():
+        play()
+        c = games.read_counters()
+        tot["moves"] += c["moves"]; tot["evals"] += c["evals"]; tot["score"] += c["score_sum"]; tot["fin"] += c["finished"]
+
+    for _ in range(warmup):
+        play()
+    for k in tot:
+        tot[k] = 0
+    launches[0] = 0
+    if sampler:
+        sampler.mark()
+    # per step: flush, event, all games to completion (one persistent launch + the init kernel), event
+    D.barrier()
+    ms = 0.0
+    for _ in range(steps):
         flush.fill_(1)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
         a.record()
-        step()
+        play()
         b.record()
         torch.cuda.synchronize()
         ms += a.elapsed_time(b)
         c = games.read_counters()
-        moves += c["moves"]; evals += c["evals"]
-        score_avg = c["score_sum"] / max(c["finished"], 1)
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
+        tot["moves"] += c["moves"]; tot["evals"] += c["evals"]; tot["score"] += c["score_sum"]; tot["fin"] += c["finished"]
+    D.barrier()
+    clocks = sampler.snapshot() if sampler else None
     e_ms, e_moves = 0.0, 0
-    for i in range(args.steps + 1):
+    for i in range(min(steps, 3) + 1):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
+        D.barrier()
         a.record()
-        c = step(e2e=True)
+        wd.copy_(w_host, non_blocking=True)                          # weights H2D from pinned memory
+        play()
+        score_host.copy_(games.score, non_blocking=True)             # per-game result D2H
+        moves_host.copy_(games.moves, non_blocking=True)
+        c = games.read_counters()
         b.record()
         torch.cuda.synchronize()
         if i:
             e_ms += a.elapsed_time(b); e_moves += c["moves"]
-    (mx, sm) = reduce_max_sum([ms, float(moves), float(evals), e_ms, float(e_moves)], ctx, world)
+    mx, sm = D.max_sum([ms, float(tot["moves"]), float(tot["evals"]), e_ms, float(e_moves), float(tot["score"]),
+                        float(tot["fin"])])
+    if D.rank != 0:
+        return None
     ms, e_ms = mx[0], mx[3]
     moves, evals, e_moves = sm[1], sm[2], sm[4]
-    if rank == 0:
-        F = F_OF_N[n]
-        peak, how = peaks()
-        E = evals / max(moves, 1)
-        bpm = 16 + 4 * F * E
-        value = moves / (ms * 1e-3)
-        ach = value / world * bpm / 1e9
-        sector = value / world * (16 + 32 * F * E) / 1e9
-        line = {"metric": "expectimax_moves_per_sec" if look else "greedy_moves_per_sec", "value": value, "unit": "moves/s",
-                "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": (f"SURVEY 8(f) rank 1: Q_agent n={n} play with look-ahead depth={args.depth} width={args.width} "
-                                        f"since_empty={args.since_empty} (game_logic.py:214-243), {B} seeded games per GPU to completion"
-                                        if look else
-                                        f"BASELINE configs[3] shape: Q_agent n={n} greedy play of {B} seeded games per GPU to "
-                                        f"completion") + ", seeded random-init weights" +
-                                       (f" + {args.pretrain} TD lock-steps" if args.pretrain else ""),
-                           "n": n, "games_per_gpu": B, "moves_per_game": moves / world / args.steps / B,
-                           "avg_score_rank0": score_avg,
-                           "l2": "a 256 MiB buffer is written between timed steps to flush L2"},
-                "clocks": clocks,
-                "e2e": {"value": e_moves / (e_ms * 1e-3), "unit": "moves/s", "h2d_bytes_per_step": wd.numel() * 4,
-                        "d2h_bytes_per_step": B * 8 + cabi.CTR_COUNT * 8},
-                "gpu_launches": None,
-                "roofline": {"bound": "hbm", "kernel": "expectimax_play_kernel (one warp per game, 16 lanes per root afterstate, "
-                                                       "depth-first subtrees, F-table gather per leaf)" if look else
-                                                       "greedy_play_kernel (4 LUT moves, F-table gather per valid afterstate, "
-                                                       "argmax, Philox spawn; whole games per launch)",
-                             "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                             "traffic": (lambda t: t * moves / world / args.steps if t and n == 6 and not args.pretrain and not look else None)(
-                                 ncu_traffic("greedy_n6_B131072_random_init", "bytes_per_move")),
-                             "peak_source": how, "bytes_per_move": bpm, "evals_per_move": E,
-                             "sector_granular_GBps": sector,
-                             "note": "algorithmic bytes = 16 + 4 F E per move; a random 4-byte gather moves a 32-byte sector, "
-                                     "sector_granular_GBps counts those"},
-                "cpu_baseline": None}
-        if world == 1:
-            from oracle import oracle as orc
-            orc.build()
-            t0 = time.perf_counter()
-            if look:
-                r = orc.play_expectimax(n, w_host.numpy(), 0, 0, min(B, max(orc.max_threads(), 8)), args.depth, args.width,
-                                        args.since_empty, threads=orc.max_threads())
-            else:
-                r = orc.play_philox(n, w_host.numpy(), seed=0, first_id=0, num=min(B, args.cpu_games), threads=orc.max_threads())
-            dt = time.perf_counter() - t0
-            line["cpu_baseline"] = {"value": r["total_moves"] / dt, "unit": "moves/s", "cores": orc.max_threads(), "kind": "port",
-                                    "sample": f"{len(r['scores'])} of the same games ({dt:.1f} s)"}
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    F = F_OF_N[n]
+    peak, how = peaks()
+    E = evals / max(moves, 1)
+    bpm = 16 + 4 * F * E
+    value = moves / (ms * 1e-3)
+    ach = value / D.world * bpm / 1e9
+    tr_b = ncu_traffic(traffic_key, "bytes_per_move") if traffic_key else None
+    nw_bytes = wd.numel() * 4
+    res = {"metric": "expectimax_moves_per_sec" if look else "greedy_moves_per_sec", "value": value, "unit": "moves/s",
+           "ms_per_step": ms / steps, "steps": steps, "warmup": warmup,
+           "config": {"workload": label, "n": n, "games_this_rank": B, "moves_per_game": moves / max(sm[6], 1),
+                      "avg_score": sm[5] / max(sm[6], 1),
+                      "l2": "a 256 MiB buffer is written between timed steps to flush L2"},
+           "clocks": clocks,
+           "e2e": {"value": e_moves / (e_ms * 1e-3) if e_ms else None, "unit": "moves/s", "h2d_bytes_per_step": nw_bytes,
+                   "d2h_bytes_per_step": B * 8 + cabi.CTR_COUNT * 8},
+           "gpu_launches": launches[0],
+           "roofline": {"bound": "hbm", "kernel": "expectimax_play_kernel" if look else "greedy_play_kernel (4 LUT moves, "
+                        "F-table gather per valid afterstate, shuffle argmax, Philox spawn; whole games per launch)",
+                        "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                        "traffic": tr_b * moves / D.world / steps if tr_b else None,
+                        "peak_source": how, "bytes_per_move": bpm, "evals_per_move": E,
+                        "sector_granular_GBps": value / D.world * (16 + 32 * F * E) / 1e9,
+                        "note": "algorithmic bytes = 16 + 4 F E per move; a random 4-byte gather moves a 32-byte sector, "
+                                "sector_granular_GBps counts those; tables of n <= 5 are L2-resident"},
+           "cpu_baseline": None}
+    if D.world == 1 and cpu_games:
+        from oracle import oracle as orc
+        orc.build()
+        t0 = time.perf_counter()
+        if look:
+            r = orc.play_expectimax(n, w_host.numpy(), 0, first_id, min(B, cpu_games), *look, threads=orc.max_threads())
+        else:
+            r = orc.play_philox(n, w_host.numpy(), seed=0, first_id=first_id, num=min(B, cpu_games), threads=orc.max_threads())
+        dt = time.perf_counter() - t0
+        k = len(r["scores"])
+        res["cpu_baseline"] = {"value": r["total_moves"] / dt, "unit": "moves/s", "cores": orc.max_threads(), "kind": "port",
+                               "sample": f"the first {k} of the same games, all host threads ({dt:.1f} s)"}
+        # the oracle doubles as the checker: the games it played must be the GPU's, score for score
+        res["oracle_match"] = bool(np.array_equal(score_host.numpy()[:k].astype(np.int64), r["scores"]))
+    return res
 
 
-def run_sweep(args):
-    """BASELINE configs[4]: `--boards` packed boards per GPU x 4 directions: afterstates, merge scores, changed /
+# --------------------------------------------------------------------------------------------- configs[4]
+def sweep_bench(D, ctx, args, m, steps, warmup, sampler=None):
+    """BASELINE configs[4]: m packed boards on this rank x 4 directions: afterstates, merge scores, changed /
     overflow flags and a Philox spawn on every changed afterstate (b2048_sweep), inputs larger than L2."""
-    import torch
-    import torch.distributed as dist
-    rank, world, local = dist_setup()
-    importlib.import_module("2048_b200")
-    from game2048 import engine
-    ctx = engine.Context.get()
-    m = args.boards
-    gen = torch.Generator(device=ctx.device).manual_seed(rank)       # cell iid: empty p=0.3 else exponent 1..11
-    boards = None
-    chunk = 1 << 22
+    torch = D.torch
+    gen = torch.Generator(device=ctx.device).manual_seed(D.rank)     # cell iid: empty p=0.3 else exponent 1..11
     parts = []
-    for i in range(0, m, chunk):
-        k = min(chunk, m - i)
+    for i in range(0, m, 1 << 22):
+        k = min(1 << 22, m - i)
         cells = torch.randint(1, 12, (k, 16), dtype=torch.int32, device=ctx.device, generator=gen)
         cells.mul_((torch.rand((k, 16), device=ctx.device, generator=gen) >= 0.3).to(torch.int32))
         parts.append(ctx.pack(cells))
+        del cells
     boards = torch.cat(parts)
     del parts
     bufs = ctx.sweep(boards, seed=0)
     host_in = torch.empty(m, dtype=torch.int64).pin_memory()
     host_in.copy_(boards)
     host_out = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in bufs]
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start(); sampler.wait_first()
-    for _ in range(args.warmup):
-        ctx.sweep(boards, seed=0, out=bufs)
-    barrier()
-    sampler.mark()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    for a, b in ev:                                              # 128 MiB in + 1.3 GB out per step: larger than L2
-        a.record()
-        ctx.sweep(boards, seed=0, first_index=rank * m, out=bufs)
-        b.record()
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    ms = sum(a.elapsed_time(b) for a, b in ev)
+    if sampler:
+        sampler.mark()
+    # 128 MiB in + 1.3 GB out per step: larger than L2, no flush needed
+    ms = timed_region(D, None, lambda: ctx.sweep(boards, seed=0, first_index=D.rank * m, out=bufs), steps, warmup)
+    clocks = sampler.snapshot() if sampler else None
     e_ms = 0.0
     for i in range(3):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
+        D.barrier()
         a.record()
         boards.copy_(host_in, non_blocking=True)
-        ctx.sweep(boards, seed=0, first_index=rank * m, out=bufs)
+        ctx.sweep(boards, seed=0, first_index=D.rank * m, out=bufs)
         for h, t in zip(host_out, bufs):
             h.copy_(t, non_blocking=True)
         b.record()
         torch.cuda.synchronize()
         if i:
             e_ms += a.elapsed_time(b) / 2
-    (mx, _) = reduce_max_sum([ms, e_ms], ctx, world)
-    if rank == 0:
-        peak, how = peaks()
-        value = world * m * args.steps / (mx[0] * 1e-3)
-        ach = value / world * 89 / 1e9
-        line = {"metric": "sweep_boards_per_sec", "value": value, "unit": "boards/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": mx[0] / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-                "config": {"workload": f"BASELINE configs[4]: {m} packed boards per GPU x 4 directions move/merge/score + spawn",
-                           "boards_per_gpu": m, "l2": "inputs + outputs (1.4 GB per step) are larger than L2"},
-                "clocks": clocks,
-                "e2e": {"value": world * m / (mx[1] * 1e-3), "unit": "boards/s", "h2d_bytes_per_step": m * 8,
-                        "d2h_bytes_per_step": m * 81},
-                "gpu_launches": args.steps,
-                "roofline": {"bound": "hbm", "kernel": "sweep_kernel (row LUT in shared memory, persistent grid)", "achieved": ach,
-                             "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                             "traffic": (lambda t: t * m if t else None)(ncu_traffic("sweep_16M", "bytes_per_board")),
-                             "peak_source": how, "bytes_per_board": 89},
-                "cpu_baseline": None}
-        if world == 1:
-            from oracle import oracle as orc
-            orc.build()
-            k = min(m, 1 << 22)
-            hb = host_in.numpy().view(np.uint64)[:k]
-            t0 = time.perf_counter()
-            orc.sweep(hb, seed=0, threads=orc.max_threads())
-            dt = time.perf_counter() - t0
-            line["cpu_baseline"] = {"value": k / dt, "unit": "boards/s", "cores": orc.max_threads(), "kind": "port",
-                                    "sample": f"the first {k} boards ({dt:.1f} s)"}
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    mx, _ = D.max_sum([ms, e_ms])
+    if D.rank != 0:
+        return None
+    peak, how = peaks()
+    value = D.world * m * steps / (mx[0] * 1e-3)
+    ach = value / D.world * 89 / 1e9
+    tr_b = ncu_traffic("sweep_16M", "bytes_per_board")
+    res = {"metric": "sweep_boards_per_sec", "value": value, "unit": "boards/s", "ms_per_step": mx[0] / steps,
+           "steps": steps, "warmup": warmup, "dtype": "u64",
+           "config": {"workload": f"BASELINE configs[4]: {m} packed boards per GPU x 4 directions move/merge/score + spawn",
+                      "boards_per_gpu": m, "l2": "inputs + outputs (1.4 GB per step) are larger than L2"},
+           "clocks": clocks,
+           "e2e": {"value": D.world * m / (mx[1] * 1e-3), "unit": "boards/s", "h2d_bytes_per_step": m * 8,
+                   "d2h_bytes_per_step": m * 81},
+           "gpu_launches": steps,
+           "roofline": {"bound": "hbm", "kernel": "sweep_kernel (row LUT in shared memory, persistent grid)", "achieved": ach,
+                        "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": tr_b * m if tr_b else None,
+                        "peak_source": how, "bytes_per_board": 89},
+           "cpu_baseline": None}
+    if D.world == 1:
+        from oracle import oracle as orc
+        orc.build()
+        k = min(m, 1 << 22)
+        hb = host_in.numpy().view(np.uint64)[:k]
+        t0 = time.perf_counter()
+        ra = orc.sweep(hb, seed=0, threads=orc.max_threads())
+        dt = time.perf_counter() - t0
+        res["cpu_baseline"] = {"value": k / dt, "unit": "boards/s", "cores": orc.max_threads(), "kind": "port",
+                               "sample": f"the first {k} boards, all host threads ({dt:.1f} s)"}
+        res["oracle_match"] = bool(np.array_equal(host_out[0].numpy().view(np.uint64)[:k], ra[0]) and
+                                   np.array_equal(host_out[3].numpy().view(np.uint64)[:k], ra[3]))
+    return res
+
+
+# --------------------------------------------------------------------------------------------- the configs object
+def run_configs(D, ctx, args, sampler):
+    """BASELINE configs[0], [2], [3], [4] in the same invocation (configs[1] is the headline)"""
+    torch = D.torch
+    from game2048 import cabi, parallel
+    out = {}
+    ks, kw = args.config_steps, 3
+    want = (lambda i: args.only_config is None or args.only_config == i)
+
+    def free():
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+
+    if want(0):       # ---- configs[0]: 1,000 games IN TOTAL, n=4, fixed pre-trained weights (strong scaling)
+        total = 1000
+        first, count = parallel.shard(total, D.world, D.rank)
+        wd = pretrained_weights(ctx, 4, 3000)
+        r = greedy_bench(D, ctx, args, 4, first, count, wd, ks, kw,
+                         f"BASELINE configs[0]: Q_agent n=4 greedy play of {total} seeded games in total from fixed weights "
+                         "(seeded init + 3000 deterministic TD lock-steps of 4096 games), to completion", sampler,
+                         traffic_key="greedy_n4_B1000_pretrained", cpu_games=total)
+        if r:
+            r.update(scaling="strong", total_games=total)
+            out["configs[0]"] = r
+        del wd
+        free()
+    if want(2):       # ---- configs[2]: n=5, 65,536 games IN TOTAL over the N GPUs, weight sync every 64 lock-steps
+        total, K = 65536, 64
+        first, count = parallel.shard(total, D.world, D.rank)
+        r, st = td_bench(D, ctx, args, 5, count, K, ks, kw, cabi.UPD_ATOMIC | cabi.UPD_MEAN, K, first_slot=first,
+                         total_slots=total, sampler=sampler, traffic_key=f"td_persist_n5_B{count}_atomic_mean")
+        if r:
+            r.update(scaling="strong", total_games=total,
+                     config={"workload": f"BASELINE configs[2]: Q_agent n=5 TD(0), {total} games in total sharded over "
+                                         f"{D.world} GPU(s) ({count} per GPU), weight sync every {K} lock-steps, "
+                                         "rule=mean, update mode=atomic; one step = one sync period",
+                             "n": 5, "games_per_gpu": count, "lock_steps_per_step": K, "sync_every": K,
+                             "l2": "21.2 MB of tables are L2-resident; 256 MiB flush between timed steps"})
+            if D.world == 1:
+                r["cpu_baseline"] = cpu_td_baseline(5, total, args.alpha, "mean", min(args.cpu_seconds, 6.0))
+            out["configs[2]"] = r
+        del st
+        free()
+    if want(3):       # ---- configs[3]: n=6 greedy, 131,072 games per GPU (1M on 8), random-init and pre-trained
+        per = 131072
+        for name, pre, key in (("random_init", 0, "greedy_n6_B131072_random_init"),
+                               ("pretrained", 3000, "greedy_n6_B131072_pretrained")):
+            wd = pretrained_weights(ctx, 6, pre)
+            r = greedy_bench(D, ctx, args, 6, D.rank * per, per, wd, min(ks, 3), kw,
+                             f"BASELINE configs[3]: Q_agent n=6 greedy play of {per} seeded games per GPU to completion, "
+                             + ("seeded random-init weights" if not pre else
+                                f"seeded init + {pre} deterministic TD lock-steps of 4096 games"), sampler,
+                             traffic_key=key, cpu_games=4096 if not pre else 256)
+            if r:
+                r.update(scaling="weak", games_per_gpu=per)
+                out.setdefault("configs[3]", {})[name] = r
+            del wd
+            free()
+    if want(4):       # ---- configs[4]: 16M boards per GPU
+        r = sweep_bench(D, ctx, args, args.boards, ks, kw, sampler)
+        if r:
+            r.update(scaling="weak")
+            out["configs[4]"] = r
+        free()
+    return out
+
+
+# --------------------------------------------------------------------------------------------- secondary workloads
+def run_greedy(args):
+    """stand-alone line for one greedy / look-ahead shape (`--workload greedy|expectimax`), same keys as the headline"""
+    D = Dist()
+    importlib.import_module("2048_b200")
+    from game2048 import engine
+    ctx = engine.Context.get()
+    n, B = args.n, args.games
+    look = (args.depth, args.width, args.since_empty) if args.workload == "expectimax" else None
+    sampler = ClockSampler(D.local)
+    if D.rank == 0:
+        sampler.start(); sampler.wait_first()
+    wd = pretrained_weights(ctx, n, args.pretrain, args.alpha)
+    label = (f"SURVEY 8(f) rank 1: Q_agent n={n} play with look-ahead depth={args.depth} width={args.width} "
+             f"since_empty={args.since_empty} (game_logic.py:214-243)" if look else
+             f"BASELINE configs[3] shape: Q_agent n={n} greedy play") + \
+            f", {B} seeded games per GPU to completion, seeded init + {args.pretrain} TD lock-steps"
+    r = greedy_bench(D, ctx, args, n, D.rank * B, B, wd, args.steps, args.warmup, label, sampler if D.rank == 0 else None,
+                     cpu_games=min(B, args.cpu_games if not look else 16), look=look)
+    if D.rank == 0:
+        sampler.stop()
+        r.update(n_gpus=D.world, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic")
+        print(json.dumps(r), flush=True)
+    D.finish()
+
+
+def run_sweep(args):
+    D = Dist()
+    importlib.import_module("2048_b200")
+    from game2048 import engine
+    ctx = engine.Context.get()
+    sampler = ClockSampler(D.local)
+    if D.rank == 0:
+        sampler.start(); sampler.wait_first()
+    r = sweep_bench(D, ctx, args, args.boards, args.steps, args.warmup, sampler if D.rank == 0 else None)
+    if D.rank == 0:
+        sampler.stop()
+        r.update(n_gpus=D.world, higher_is_better=True, scaling="weak", vs_baseline=None, data="synthetic")
+        print(json.dumps(r), flush=True)
+    D.finish()
 
 
 def main():

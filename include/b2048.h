@@ -172,6 +172,8 @@ enum {
     B2048_CTR_ACTIVE = 7,   /* greedy_play: slots still playing after the call (overwritten) */
     B2048_CTR_LOG = 8,      /* finished-game records appended to fin_log (host may reset to 0) */
     B2048_CTR_QUEUE = 9,    /* greedy_play: next slot to hand out (work queue of the running launch, overwritten) */
+    B2048_CTR_FAULT = 10,   /* != 0: a persistent launch gave up at a grid barrier (a CTA was lost); the results of
+                               that call and the workspace are invalid.  Never reset by the kernels. */
     B2048_CTR_COUNT = 16
 };
 
@@ -242,6 +244,9 @@ int b2048_td_phase_a(int n, const float *weights, const uint32_t *lut, const b20
  * (bit-identical in the DETERMINISTIC modes).  mode | B2048_RUN_STEPWISE (or B2048_UPD_SORTED, or a device
  * without cooperative launch) enqueues b2048_td_step `steps` times instead (3 launches per lock-step). */
 #define B2048_RUN_STEPWISE 8
+/* mode | B2048_RUN_GENERIC: the persistent kernel in its generic slot layout (rounds over the staging arrays and per-CTA
+ * key lists) even where the one-round register layout would fit; same results, used by the parity tests */
+#define B2048_RUN_GENERIC 16
 /* number of kernel launches b2048_td_run(n, B slots, mode, steps) enqueues on this device (1 = persistent) */
 int64_t b2048_td_run_launches(int n, int64_t B, int mode, int steps);
 int b2048_td_run(int n, float *weights, float *delta, const uint32_t *lut, const b2048_games_t *g, float alpha,
@@ -264,6 +269,39 @@ int b2048_delta_pack_diff(const float *weights, const float *w_sync, float *pack
                           b2048_stream_t stream);
 int b2048_delta_apply(float *weights, float *w_sync, float *delta, const float *delta_sum, const float *contributors,
                       int64_t count, b2048_stream_t stream);
+
+
+/* The same exchange with one BIT per weight instead of a float indicator (4 + 1/8 bytes per weight and rank on the wire
+ * instead of 8): delta [count] = weights - w_sync, bits [ceil(count/32)] bit i%32 of word i/32 = (weights[i] != w_sync[i]);
+ * allreduce(sum) of delta and allgather of the bit planes over the ranks; then with bits_all = [world, ceil(count/32)]:
+ *   w_sync[k] += delta_sum[k] / max(1, number of ranks whose bit k is set);  weights[k] = w_sync[k]. */
+int b2048_delta_pack_bits(const float *weights, const float *w_sync, float *delta, uint32_t *bits, int64_t count,
+                          b2048_stream_t stream);
+int b2048_delta_apply_bits(float *weights, float *w_sync, const float *delta_sum, const uint32_t *bits_all, int world,
+                           int64_t count, b2048_stream_t stream);
+
+/* The whole exchange as ONE kernel per rank over NVLink / NVSwitch peer memory (no NCCL): rank r reduces the r-th
+ * contiguous slice of the weights -- remote loads of every rank's weights and w_sync, sum of the deltas in rank order,
+ * contributor count, w_sync + sum / max(1, contributors) -- and stores the result into weights and w_sync of EVERY rank,
+ * so all replicas hold the owner's bits.  w / w_sync / flags: the buffers of rank q as mapped into THIS process (CUDA IPC
+ * or symmetric memory; entry `rank` = the local buffers); each flags[q] is B2048_PEER_FLAG_WORDS zero-initialised uint32.
+ * Ranks rendezvous inside the kernel through flags: every rank must call with the same count and the same epoch, a
+ * value that increases by one per call starting at 1.  max_ctas: grid cap (0 = 4 per SM); all ranks' kernels must be
+ * resident at the same time (one per GPU; several emulated ranks on ONE GPU need streams and a cap).
+ * flags[rank][B2048_PEER_FAULT] != 0 afterwards: a peer never arrived (2^26 polls), the sync did not complete. */
+#define B2048_MAX_PEERS 16
+#define B2048_PEER_ARRIVE 0
+#define B2048_PEER_DONE 16
+#define B2048_PEER_TICKET 32
+#define B2048_PEER_FAULT 33
+#define B2048_PEER_FLAG_WORDS 64
+typedef struct b2048_peers {
+    float *w[B2048_MAX_PEERS];
+    float *w_sync[B2048_MAX_PEERS];
+    uint32_t *flags[B2048_MAX_PEERS];
+    int world, rank;
+} b2048_peers_t;
+int b2048_sync_peers(const b2048_peers_t *peers, int64_t count, uint32_t epoch, int max_ctas, b2048_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -419,14 +419,18 @@ def test_td_lockstep_deterministic_bit_exact(eng, orc, fx, n, B):
 @pytest.mark.parametrize("n,B,steps,force", [(4, 64, 200, "generic"), (5, 5000, 60, None), (6, 700, 40, None),
                                              (2, 4096, 50, None), (3, 4096, 40, None), (5, 17000, 30, None),
                                              (4, 3000, 80, None), (3, 1000, 60, None), (2, 2000, 50, None),
-                                             (4, 8, 300, None)])
+                                             (4, 8, 300, None),
+                                             # BASELINE configs[2] shapes: n=5 with 65,536 games on 1 / 2 GPUs
+                                             (5, 32768, 12, None), (5, 65536, 8, None),
+                                             # n=6 in the generic layout (more slots per CTA than one round; forced)
+                                             (6, 4096, 12, None), (6, 300, 40, "generic")])
 def test_td_persistent_paths_bit_exact(eng, orc, fx, monkeypatch, n, B, steps, force):
     """b2048_td_run's persistent kernel gives the oracle's bits in the deterministic modes in both slot layouts:
     one phase-B round per CTA with the state in registers ((6, 700), (4, 3000), (3, 1000), (2, 2000), (4, 8)), and
-    the generic layout (rounds over global staging and key lists: forced, or the larger shapes)."""
+    the generic layout (rounds over global staging and key lists: forced with B2048_RUN_GENERIC, or the larger
+    shapes, among them n=5 at 32,768 / 65,536 games and n=6 at 4,096)."""
     ctx, engine, cabi = eng
-    if force == "generic":
-        monkeypatch.setenv("B2048_PERSIST_GENERIC", "1")
+    layout = cabi.RUN_GENERIC if force == "generic" else 0
     for rule, mode, alpha in ((4, cabi.UPD_DETERMINISTIC | cabi.UPD_MEAN, 0.25),
                               (3, cabi.UPD_DETERMINISTIC | cabi.UPD_SUM, 0.25 / B)):
         w0 = fx.flat(fx.init_weights32(n, 41)).astype(np.float32)
@@ -435,7 +439,7 @@ def test_td_persistent_paths_bit_exact(eng, orc, fx, monkeypatch, n, B, steps, f
         ls.run(steps)
         wd = ctx.to_device(w0)
         games = engine.GameBatch(B, seed=91, ctx=ctx).init()
-        tr = engine.TDTrainer(ctx, n, wd, games, alpha, mode)
+        tr = engine.TDTrainer(ctx, n, wd, games, alpha, mode | layout)
         tr.run(steps // 3)
         tr.run(steps - steps // 3)                                        # a second launch resumes from memory
         h, c = games.to_host(), games.read_counters()

@@ -27,8 +27,8 @@ class OracleOps:
     def weights(self, flat):
         return torch.from_numpy(np.array(flat, dtype=np.float32))
 
-    def zeros_like_weights(self, w, mult=1):
-        return torch.zeros(w.numel() * mult, dtype=torch.float32)
+    def zeros(self, count, dtype=torch.float32):
+        return torch.zeros(count, dtype=dtype)
 
     def trainer(self, n, w, delta, B, alpha, mode, seed, first_id, id_stride):
         rule = 4 if mode & 2 else 3                         # DETERMINISTIC | MEAN / SUM
@@ -43,15 +43,19 @@ class OracleOps:
     def counters(self, ls):
         return {"updates": ls.n_updates, "moves": ls.n_moves, "finished": int(ls.fin[0])}
 
-    def delta_pack(self, w, w_sync, packed):
+    def delta_pack_bits(self, w, w_sync, delta, bits):
+        """b2048_delta_pack_bits restated: float32 difference + one bit per weight, 32 per int32 word"""
         n = w.numel()
-        packed[:n] = w - w_sync
-        packed[n:] = (w != w_sync).float()
+        delta.copy_(w - w_sync)
+        moved = np.zeros(bits.numel() * 32, np.uint8)
+        moved[:n] = (w != w_sync).numpy()
+        bits.copy_(torch.from_numpy(np.packbits(moved, bitorder="little").view(np.int32)))
 
-    def delta_apply(self, w, w_sync, packed):
+    def delta_apply_bits(self, w, w_sync, delta_sum, bits_all, world):
         n = w.numel()
-        c = packed[n:].clamp(min=1.0)
-        w_sync += packed[:n] / c
+        planes = np.unpackbits(bits_all.numpy().view(np.uint8).reshape(world, -1), axis=1, bitorder="little")[:, :n]
+        c = torch.from_numpy(planes.sum(axis=0).astype(np.float32)).clamp(min=1.0)
+        w_sync += delta_sum / c
         w.copy_(w_sync)
 
     def greedy(self, n, w, seed, first_id, count, limit_tile=0):
@@ -78,10 +82,15 @@ def _worker(rank, world, port, out_dir):
     from test_parallel_gloo import OracleOps
     n, B = 2, 6
     w0 = fx.flat(fx.init_weights32(n, 4))
-    tr = parallel.ShardedTrainer(n, w0, B, alpha=0.25, mode=3, seed=9, sync_every=5, ops=OracleOps())
+    # rank 1 is handed different tables on purpose: the constructor broadcasts rank 0's
+    tr = parallel.ShardedTrainer(n, w0 if rank == 0 else w0[::-1].copy(), B, alpha=0.25, mode=3, seed=9, sync_every=5,
+                                 ops=OracleOps())
+    assert tr.sync_impl == "nccl" and tr.replicas_identical()
     tr.run(12)                                               # syncs after lock-steps 5 and 10, 2 steps pending
     mid = tr.w.clone()
-    tr.sync()                                                # flush the pending delta
+    assert not tr.replicas_identical()
+    tr.run(0, final_sync=True)                               # flush the pending delta
+    assert tr.replicas_identical()
     c = tr.counters()
     stats = parallel.greedy_sharded(n, w0, 11, seed=3, ops=OracleOps())
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), w=tr.w.numpy(), mid=mid.numpy(), syncs=tr.syncs,
