@@ -78,8 +78,19 @@ __host__ __device__ inline uint32_t lut_entry(uint32_t line)
 // ------------------------------------------------------------------------------------------------
 // board symmetries (np.transpose / np.rot90 views of r_learning.py:207-214, game_logic.py:138-141)
 // ------------------------------------------------------------------------------------------------
+// On the device the symmetries work on the two 32-bit halves (hi = rows 0-1, lo = rows 2-3) with byte permutes (PRMT)
+// for everything that moves whole bytes: transpose 10 instructions instead of ~24, flip_h 8 instead of ~16, flip_v 2.
 __host__ __device__ __forceinline__ uint64_t transpose(uint64_t x)
 {
+#ifdef __CUDA_ARCH__
+    uint32_t lo = uint32_t(x), hi = uint32_t(x >> 32);
+    // stage 1: transpose the nibbles inside every 2x2 block (same masks for both halves)
+    lo = (lo & 0xF0F00F0Fu) | ((lo & 0x0000F0F0u) << 12) | ((lo & 0x0F0F0000u) >> 12);
+    hi = (hi & 0xF0F00F0Fu) | ((hi & 0x0000F0F0u) << 12) | ((hi & 0x0F0F0000u) >> 12);
+    // stage 2: swap the off-diagonal 2x2 blocks = bytes B1<->B4, B3<->B6 of [B0 B1 B2 B3 | B4 B5 B6 B7]
+    const uint32_t nh = __byte_perm(hi, lo, 0x3715), nl = __byte_perm(hi, lo, 0x2604);
+    return (uint64_t(nh) << 32) | nl;
+#else
     uint64_t a1 = x & 0xF0F00F0FF0F00F0FULL;
     uint64_t a2 = x & 0x0000F0F00000F0F0ULL;
     uint64_t a3 = x & 0x0F0F00000F0F0000ULL;
@@ -88,19 +99,31 @@ __host__ __device__ __forceinline__ uint64_t transpose(uint64_t x)
     uint64_t b2 = a & 0x00FF00FF00000000ULL;
     uint64_t b3 = a & 0x00000000FF00FF00ULL;
     return b1 | (b2 >> 24) | (b3 << 24);
+#endif
 }
 
 // mirror the columns (reverse every row)
 __host__ __device__ __forceinline__ uint64_t flip_h(uint64_t x)
 {
+#ifdef __CUDA_ARCH__
+    uint32_t lo = uint32_t(x), hi = uint32_t(x >> 32);
+    lo = ((lo << 4) & 0xF0F0F0F0u) | ((lo >> 4) & 0x0F0F0F0Fu);       // swap the nibbles of every byte
+    hi = ((hi << 4) & 0xF0F0F0F0u) | ((hi >> 4) & 0x0F0F0F0Fu);
+    return (uint64_t(__byte_perm(hi, 0, 0x2301)) << 32) | __byte_perm(lo, 0, 0x2301);   // and the bytes of every row
+#else
     return ((x & 0xF000F000F000F000ULL) >> 12) | ((x & 0x0F000F000F000F00ULL) >> 4) |
            ((x & 0x00F000F000F000F0ULL) << 4) | ((x & 0x000F000F000F000FULL) << 12);
+#endif
 }
 
 // mirror the rows (reverse the row order)
 __host__ __device__ __forceinline__ uint64_t flip_v(uint64_t x)
 {
+#ifdef __CUDA_ARCH__
+    return (uint64_t(__byte_perm(uint32_t(x), 0, 0x1032)) << 32) | __byte_perm(uint32_t(x >> 32), 0, 0x1032);
+#else
     return (x >> 48) | ((x >> 16) & 0x00000000FFFF0000ULL) | ((x << 16) & 0x0000FFFF00000000ULL) | (x << 48);
+#endif
 }
 
 __host__ __device__ __forceinline__ uint32_t reverse_line(uint32_t r)

@@ -572,7 +572,7 @@ def test_argument_errors(eng):
     tr = engine.TDTrainer(ctx, 4, w, games, 0.25, cabi.UPD_ATOMIC | cabi.UPD_MEAN)
     assert L.b2048_td_run(4, engine.dptr(w), None, engine.dptr(ctx.lut), C.byref(games.c), C.c_float(0.25), 2, 5,
                           engine.dptr(tr.upd_board), engine.dptr(tr.upd_dw), None, 0, None) == -3   # no workspace
-    assert L.b2048_td_run(4, engine.dptr(w), None, engine.dptr(ctx.lut), C.byref(games.c), C.c_float(0.25), 16, 5,
+    assert L.b2048_td_run(4, engine.dptr(w), None, engine.dptr(ctx.lut), C.byref(games.c), C.c_float(0.25), 32, 5,
                           engine.dptr(tr.upd_board), engine.dptr(tr.upd_dw), engine.dptr(tr.work), tr.work.numel(),
                           None) == -1                                                               # unknown mode bit
     # look-ahead entry points
