@@ -1367,6 +1367,42 @@ __device__ __forceinline__ bool grid_barrier(uint32_t *bar, uint32_t &target, ui
     return grid_wait(bar, target, fault);
 }
 
+// Weight exchange with the other GPUs from INSIDE the persistent launch (b2048_td_run_peers), called by every thread of
+// every CTA right after the grid barrier that completes W_{t+1}: announce (this rank's lock-steps are done, its weight
+// stores are ordered before the signal), wait for every peer's announcement, reduce this rank's slice over peer memory
+// with all CTAs (peer_reduce_slice), grid barrier, tell the peers that the stores are out, wait for theirs.  The game
+// state stays in registers and the launch goes on with the next lock-step: no relaunch, no separate sync kernel.
+__device__ __forceinline__ bool peer_sync_in_kernel(const PeerSync &ps, uint32_t epoch, uint32_t *bar, uint32_t &bar_target,
+                                                    uint64_t *fault)
+{
+    __shared__ int s_ok;
+    const b2048_peers_t &P = ps.peers;
+    const int W = P.world, rank = P.rank;
+    uint32_t *mine = P.flags[rank];
+    if (threadIdx.x == 0) s_ok = 1;
+    __syncthreads();
+    if (blockIdx.x == 0 && int(threadIdx.x) < W) {
+        __threadfence_system();
+        st_release_sys(P.flags[threadIdx.x] + B2048_PEER_ARRIVE + rank, epoch);
+    }
+    if (int(threadIdx.x) < W && !wait_epoch(mine + B2048_PEER_ARRIVE + threadIdx.x, epoch)) s_ok = 0;
+    __syncthreads();
+    if (s_ok) peer_reduce_slice(P, ps.count, int64_t(blockIdx.x) * blockDim.x + threadIdx.x, int64_t(gridDim.x) * blockDim.x);
+    __threadfence_system();                                   // this thread's remote stores are performed
+    if (!grid_barrier(bar, bar_target, fault)) return false;  // ... and everybody else's of this rank
+    if (blockIdx.x == 0 && int(threadIdx.x) < W && s_ok) st_release_sys(P.flags[threadIdx.x] + B2048_PEER_DONE + rank, epoch);
+    if (int(threadIdx.x) < W && s_ok && !wait_epoch(mine + B2048_PEER_DONE + threadIdx.x, epoch)) s_ok = 0;
+    __syncthreads();
+    if (!s_ok) {
+        if (threadIdx.x == 0) {
+            atomicExch(reinterpret_cast<unsigned long long *>(fault), 1ULL);
+            mine[B2048_PEER_FAULT] = epoch;
+        }
+        return false;
+    }
+    return true;
+}
+
 // ---- dense small-exponent key space --------------------------------------------------------------
 __host__ __device__ constexpr int small_tables(int n) { return n == 6 ? 21 : num_feat(n); }   // base-16 tables only
 __host__ __device__ constexpr int tuple_cells(int n, int i) { return n <= 3 ? n : i < 17 ? 4 : i < 21 ? 5 : 6; }
@@ -1442,10 +1478,10 @@ constexpr int PERSIST_TILE = 32;           // FAST path: at most this many slots
 // registers across the barrier and applies / flushes them itself: no lists, no cursors, no global round trip
 // except the weight gathers and the atomics.  Otherwise slots are processed in rounds through the b2048_td_step
 // staging arrays and per-CTA key lists in global memory.
-template <int N, bool EXACT, bool MEAN, bool DIRECT, bool FAST>
+template <int N, bool EXACT, bool MEAN, bool DIRECT, bool FAST, bool PEERS>
 __global__ void __launch_bounds__(PERSIST_THREADS, 1)
 td_persist_kernel(PersistBuffers pb, PersistCtrl *ctrl, const uint32_t *__restrict__ lut, b2048_games_t g, float alpha,
-                  int steps, uint64_t *upd_board, float *upd_dw, int spc, long long *tlog)
+                  int steps, uint64_t *upd_board, float *upd_dw, int spc, long long *tlog, const __grid_constant__ PeerSync ps)
 {
     // tlog (debug, B2048_PERSIST_TLOG): clock64 at the phase boundaries of the last 16 steps, per CTA
     constexpr int F = num_feat(N);
@@ -1831,6 +1867,13 @@ td_persist_kernel(PersistBuffers pb, PersistCtrl *ctrl, const uint32_t *__restri
             if (!grid_wait(&ctrl->bar, bar_target, fault)) return;
         }
         if (tl) tl[6] = clock64();
+        // ---- multi-GPU: every sync_every lock-steps the replicas exchange what their weights moved by, in this launch
+        if (PEERS && ps.sync_every > 0) {                     // (W_{t+1} is complete here in every mode)
+            const int done = ps.since_sync + step + 1;        // lock-steps since the sync before this launch
+            if (done % ps.sync_every == 0 &&
+                !peer_sync_in_kernel(ps, ps.epoch + uint32_t(done / ps.sync_every) - 1u, &ctrl->bar, bar_target, fault))
+                return;
+        }
     }
     if (FAST && a_in && a_dir == 0 && st_dirty) slot_store(g, slot0 + a_slot, st);
     flush_counters(g.counters, c);
@@ -1919,10 +1962,10 @@ int td_update_impl(float *weights, float *delta, const uint64_t *boards, const f
 }
 
 // ---- persistent trainer launch ---------------------------------------------------------------------
-template <int N, bool EXACT, bool MEAN, bool DIRECT, bool FAST>
+template <int N, bool EXACT, bool MEAN, bool DIRECT, bool FAST, bool PEERS>
 int launch_persist(int grid, cudaStream_t st, void **args)
 {
-    auto kern = td_persist_kernel<N, EXACT, MEAN, DIRECT, FAST>;
+    auto kern = td_persist_kernel<N, EXACT, MEAN, DIRECT, FAST, PEERS>;
     const int smem = small_count(N) * (EXACT ? 14 : 10);           // sums, counts, dirty list
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);   // per call: no cache
     if (e != cudaSuccess) return int(e);
@@ -1939,19 +1982,19 @@ int launch_persist(int grid, cudaStream_t st, void **args)
     return e == cudaSuccess ? 0 : int(e);
 }
 
-template <int N, bool FAST>
+template <int N, bool FAST, bool PEERS>
 int launch_persist_mode(bool det, bool mean, int grid, cudaStream_t st, void **args)
 {
-    if (!det && !mean) return launch_persist<N, false, false, true, FAST>(grid, st, args);
-    if (!det) return launch_persist<N, false, true, false, FAST>(grid, st, args);
-    if (mean) return launch_persist<N, true, true, false, FAST>(grid, st, args);
-    return launch_persist<N, true, false, false, FAST>(grid, st, args);
+    if (!det && !mean) return launch_persist<N, false, false, true, FAST, PEERS>(grid, st, args);
+    if (!det) return launch_persist<N, false, true, false, FAST, PEERS>(grid, st, args);
+    if (mean) return launch_persist<N, true, true, false, FAST, PEERS>(grid, st, args);
+    return launch_persist<N, true, false, false, FAST, PEERS>(grid, st, args);
 }
 
 template <int N>
 int td_run_persistent(float *weights, float *delta, const uint32_t *lut, const b2048_games_t *g, float alpha,
                       int mode, int steps, uint64_t *upd_board, float *upd_dw, void *work, size_t work_bytes,
-                      cudaStream_t st)
+                      const PeerSync *peer_sync, cudaStream_t st)
 {
     const bool det = mode & B2048_UPD_DETERMINISTIC, mean = mode & B2048_UPD_MEAN;
     const int64_t B = g->B;
@@ -1977,11 +2020,16 @@ int td_run_persistent(float *weights, float *delta, const uint32_t *lut, const b
         else cudaMemsetAsync(tlog, 0, size_t(grid) * 16 * 8 * sizeof(long long), st);
     }
 #endif
-    void *args[] = {&pb, &ctrl, &lut, &games, &alpha, &steps, &upd_board, &upd_dw, &spc_i, &tlog};
+    PeerSync ps{};                                                 // sync_every = 0: single GPU
+    if (peer_sync) ps = *peer_sync;
+    void *args[] = {&pb, &ctrl, &lut, &games, &alpha, &steps, &upd_board, &upd_dw, &spc_i, &tlog, &ps};
     // FAST: one phase-B round per lock-step, state in registers, staging and key list in shared memory
     const bool fast = spc <= PERSIST_THREADS / num_feat(N) && spc <= PERSIST_TILE && !(mode & B2048_RUN_GENERIC);
-    const int rc = fast ? launch_persist_mode<N, true>(det, mean, grid, st, args)
-                        : launch_persist_mode<N, false>(det, mean, grid, st, args);
+    const bool with_peers = ps.sync_every > 0;
+    const int rc = fast ? (with_peers ? launch_persist_mode<N, true, true>(det, mean, grid, st, args)
+                                      : launch_persist_mode<N, true, false>(det, mean, grid, st, args))
+                        : (with_peers ? launch_persist_mode<N, false, true>(det, mean, grid, st, args)
+                                      : launch_persist_mode<N, false, false>(det, mean, grid, st, args));
 #ifdef B2048_PERSIST_TLOG
     if (tlog) {
         std::vector<long long> h(size_t(grid) * 16 * 8);

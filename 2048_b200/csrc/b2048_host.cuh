@@ -110,6 +110,100 @@ inline WorkLayout work_layout(int n, int64_t m, int mode)
     return L;
 }
 
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ float4 ld_sys_f4(const float *p)
+{
+    float4 v;
+    asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ float ld_sys_f1(const float *p)
+{
+    float v;
+    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// spin until *flag has reached `epoch` (wrap-safe); false after ~2^26 polls: a peer is gone
+__device__ __forceinline__ bool wait_epoch(const uint32_t *flag, uint32_t epoch)
+{
+    for (uint32_t polls = 0; int32_t(ld_acquire_sys(flag) - epoch) < 0;)
+        if (++polls > (1u << 26)) return false;
+    return true;
+}
+
+
+// One pass of rank P.rank over ITS contiguous slice of the weights (see peer_sync_kernel): remote loads of every rank's
+// w and w_sync, sum of the deltas in rank order, contributor count, result stored into w and w_sync of every rank.
+// Run-time world size (the persistent trainer calls it from inside its lock-step loop); `nthreads` threads with ids
+// 0 <= tid < nthreads share the slice.
+__device__ __forceinline__ void peer_reduce_slice(const b2048_peers_t &P, int64_t count, int64_t tid, int64_t nthreads)
+{
+    const int W = P.world, rank = P.rank;
+    const int64_t n4 = count >> 2;
+    const int64_t per = (n4 + W - 1) / W;
+    const int64_t lo = rank * per, hi = (lo + per < n4) ? lo + per : n4;
+    for (int64_t v = lo + tid; v < hi; v += nthreads) {
+        float sum[4] = {0.0f, 0.0f, 0.0f, 0.0f}, base[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        uint32_t c[4] = {0, 0, 0, 0};
+#pragma unroll 2
+        for (int q = 0; q < W; q++) {                                      // rank order: a fixed association
+            const float4 a = ld_sys_f4(P.w[q] + 4 * v), b = ld_sys_f4(P.w_sync[q] + 4 * v);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const float d = __fsub_rn(av[k], bv[k]);
+                sum[k] = q == 0 ? d : __fadd_rn(sum[k], d);
+                c[k] += av[k] != bv[k];
+                if (q == rank) base[k] = bv[k];
+            }
+        }
+        float r[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) r[k] = __fadd_rn(base[k], c[k] > 1u ? __fdiv_rn(sum[k], float(c[k])) : sum[k]);
+        const float4 out = make_float4(r[0], r[1], r[2], r[3]);
+        for (int q = 0; q < W; q++) {
+            *reinterpret_cast<float4 *>(P.w[q] + 4 * v) = out;
+            *reinterpret_cast<float4 *>(P.w_sync[q] + 4 * v) = out;
+        }
+    }
+    if (rank == W - 1)                                                     // count % 4 trailing weights
+        for (int64_t i = (n4 << 2) + tid; i < count; i += nthreads) {
+            float sum = 0.0f, base = 0.0f;
+            uint32_t c = 0;
+            for (int q = 0; q < W; q++) {
+                const float av = ld_sys_f1(P.w[q] + i), bv = ld_sys_f1(P.w_sync[q] + i);
+                const float d = __fsub_rn(av, bv);
+                sum = q == 0 ? d : __fadd_rn(sum, d);
+                c += av != bv;
+                if (q == rank) base = bv;
+            }
+            const float out = __fadd_rn(base, c > 1u ? __fdiv_rn(sum, float(c)) : sum);
+            for (int q = 0; q < W; q++) { P.w[q][i] = out; P.w_sync[q][i] = out; }
+        }
+}
+
+// in-kernel weight exchange of the persistent trainer (b2048_td_run_peers): which lock-steps end with a sync
+struct PeerSync {
+    b2048_peers_t peers;
+    int64_t count;          // weights
+    int sync_every;         // 0 = never (single GPU)
+    int since_sync;         // lock-steps already done since the last sync when the launch starts
+    uint32_t epoch;         // epoch of the first sync of this launch
+};
+
 bool games_ok(const b2048_games_t *g)
 {
     return g && g->B >= 0 && g->board && g->score && g->moves && g->game_id && g->state && g->old_label && g->flags &&
@@ -134,7 +228,7 @@ struct b2048_agent_ops {
                       float *trace_dw, uint16_t *trace_spawn, int64_t trace_len, cudaStream_t st);
     int (*td_run_persistent)(float *w, float *delta, const uint32_t *lut, const b2048_games_t *g, float alpha, int mode,
                              int steps, uint64_t *upd_board, float *upd_dw, void *work, size_t work_bytes,
-                             cudaStream_t st);
+                             const PeerSync *peer_sync, cudaStream_t st);
     int (*look_forward)(const float *w, const uint32_t *lut, const uint64_t *boards, const uint64_t *game_id,
                         const uint32_t *move_no, const uint8_t *root_dir, int64_t m, int depth, int width,
                         int since_empty, uint64_t seed, float *value, cudaStream_t st);

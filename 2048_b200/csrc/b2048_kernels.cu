@@ -327,40 +327,6 @@ __global__ void delta_apply_bits_kernel(float *__restrict__ w, float *__restrict
 // receives the owner's bits.  Ranks rendezvous through epoch flags in peer memory: arrive[q] before the first remote
 // load (rank q has finished the lock-steps before its sync kernel and will not touch w until the sync is over), done[q]
 // after the last remote store has been fenced (the last CTA to finish signals and waits, the others just exit).
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p)
-{
-    uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-
-__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v)
-{
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-__device__ __forceinline__ float4 ld_sys_f4(const float *p)
-{
-    float4 v;
-    asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
-    return v;
-}
-
-__device__ __forceinline__ float ld_sys_f1(const float *p)
-{
-    float v;
-    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
-    return v;
-}
-
-// spin until *flag has reached `epoch` (wrap-safe); false after ~2^26 polls: a peer is gone
-__device__ __forceinline__ bool wait_epoch(const uint32_t *flag, uint32_t epoch)
-{
-    for (uint32_t polls = 0; int32_t(ld_acquire_sys(flag) - epoch) < 0;)
-        if (++polls > (1u << 26)) return false;
-    return true;
-}
-
 constexpr int PEER_THREADS = 256;
 
 template <int W>   // W = world size (compile-time: the per-rank loads are all issued before the first use)
@@ -676,7 +642,7 @@ int b2048_td_run(int n, float *weights, float *delta, const uint32_t *lut, const
     mode &= 7;
     if (!stepwise && cooperative_ok()) {
         int rc = agent_ops(n)->td_run_persistent(weights, delta, lut, g, alpha, mode | layout, steps, upd_board, upd_dw, work,
-                                                 work_bytes, S(stream));
+                                                 work_bytes, nullptr, S(stream));
         if (rc != B2048_ENOTSUP) return rc;
     }
     for (int s = 0; s < steps; s++) {
@@ -685,6 +651,30 @@ int b2048_td_run(int n, float *weights, float *delta, const uint32_t *lut, const
         if (rc) return rc;
     }
     return 0;
+}
+
+int b2048_td_run_peers(int n, float *weights, const uint32_t *lut, const b2048_games_t *g, float alpha, int mode, int steps,
+                       uint64_t *upd_board, float *upd_dw, void *work, size_t work_bytes, const b2048_peers_t *peers,
+                       int sync_every, int since_sync, uint32_t epoch, b2048_stream_t stream)
+{
+    if (steps < 0 || (mode & ~(7 | B2048_RUN_GENERIC)) || (mode & B2048_UPD_SORTED)) return B2048_EINVAL;
+    if (!games_ok(g) || num_feat(n) < 0 || !weights || !lut || !upd_board || !upd_dw) return B2048_EINVAL;
+    if (!peers || peers->world < 1 || peers->world > B2048_MAX_PEERS || peers->rank < 0 || peers->rank >= peers->world ||
+        sync_every < 1 || since_sync < 0 || since_sync >= sync_every || epoch == 0)
+        return B2048_EINVAL;
+    for (int q = 0; q < peers->world; q++)
+        if (!peers->w[q] || !peers->w_sync[q] || !peers->flags[q]) return B2048_EINVAL;
+    if (peers->w[peers->rank] != weights) return B2048_EINVAL;      // the trained buffer must be the mapped one
+    if (steps == 0) return 0;
+    if (g->B == 0 || !cooperative_ok()) return B2048_ENOTSUP;       // every rank needs the persistent launch
+    PeerSync ps{};
+    ps.peers = *peers;
+    ps.count = table_offset(n, num_feat(n));
+    ps.sync_every = sync_every;
+    ps.since_sync = since_sync;
+    ps.epoch = epoch;
+    return agent_ops(n)->td_run_persistent(weights, nullptr, lut, g, alpha, mode, steps, upd_board, upd_dw, work, work_bytes,
+                                           &ps, S(stream));
 }
 
 int64_t b2048_td_run_launches(int n, int64_t B, int mode, int steps)

@@ -82,6 +82,8 @@ SIGNATURES = {
     "b2048_delta_pack_bits": (_int, [_vp, _vp, _vp, _vp, _i64, _vp]),
     "b2048_delta_apply_bits": (_int, [_vp, _vp, _vp, _vp, _int, _i64, _vp]),
     "b2048_sync_peers": (_int, [_PP, _i64, C.c_uint32, _int, _vp]),
+    "b2048_td_run_peers": (_int, [_int, _vp, _vp, _GP, _f32, _int, _int, _vp, _vp, _vp, _sz, _PP, _int, _int, C.c_uint32,
+                                  _vp]),
 }
 
 _lib = None

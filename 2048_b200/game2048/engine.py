@@ -340,6 +340,20 @@ class TDTrainer:
                                            dptr(self.upd_dw), self.games.B, self.mode & 7, dptr(self.work),
                                            self.work.numel(), cur_stream()), "td_update")
 
+    def run_peers(self, steps, peers, sync_every, since_sync, epoch):
+        """`steps` lock-steps in ONE persistent launch with the multi-GPU weight exchange inside it (b2048_td_run_peers):
+        a sync after every lock-step that completes a period of `sync_every`.  Returns False when this device / batch
+        cannot take the persistent kernel (the caller then alternates run() and the stand-alone sync kernel)."""
+        rc = self.ctx.lib.b2048_td_run_peers(self.n, dptr(self.w), dptr(self.ctx.lut), C.byref(self.games.c), self.alpha,
+                                             self.mode & ~cabi.RUN_STEPWISE, int(steps), dptr(self.upd_board),
+                                             dptr(self.upd_dw), dptr(self.work), self.work.numel(), C.byref(peers),
+                                             int(sync_every), int(since_sync), int(epoch), cur_stream())
+        if rc == -2:                                             # B2048_ENOTSUP
+            return False
+        check(rc, "td_run_peers")
+        self.launches += 1
+        return True
+
     def run(self, steps):
         """`steps` lock-steps without host work in between: one persistent cooperative kernel (default), or
         3 launches per lock-step with mode | RUN_STEPWISE"""

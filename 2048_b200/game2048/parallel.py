@@ -6,9 +6,11 @@ from w_sync.  Greedy play needs no collective at all (Philox streams are keyed b
 reproduce the 1-rank games exactly); only the final per-game statistics are gathered.
 
 Two implementations of the exchange (same formula; each leaves the replicas bit-identical):
-  "p2p"   ONE fused kernel per rank over NVLink / NVSwitch peer memory (b2048_sync_peers): the weights and w_sync of
-          every rank are symmetric-memory allocations mapped into every process; rank r reduces slice r from remote
-          loads and stores the result into every replica.  No NCCL call, no message buffers.
+  "p2p"   over NVLink / NVSwitch peer memory: the weights and w_sync of every rank are symmetric-memory allocations
+          mapped into every process; rank r reduces slice r from remote loads and stores the result into every replica.
+          No NCCL call, no message buffers.  With `fused` (default) the exchange runs INSIDE the persistent training
+          launch (b2048_td_run_peers: run(S) is one kernel per rank however many syncs fall into it); otherwise, or
+          for a flush between launches, it is one stand-alone kernel per sync (b2048_sync_peers).
   "nccl"  b2048_delta_pack_bits -> allreduce(sum) of the float32 deltas + allgather of the one-bit-per-weight
           contributor planes (4.125 bytes per weight on the wire instead of the 8 of a float indicator) ->
           b2048_delta_apply_bits.  The portable path, and the one the CPU tier exercises under gloo.
@@ -59,6 +61,9 @@ class CudaOps:
 
     def run(self, trainer, steps):
         trainer.run(steps)
+
+    def run_peers(self, trainer, steps, peers, sync_every, since_sync, epoch):
+        return trainer.run_peers(steps, peers, sync_every, since_sync, epoch)
 
     def counters(self, trainer):
         return trainer.games.read_counters()
@@ -131,7 +136,7 @@ class ShardedTrainer:
     `final_sync` is set, so that the replicas are identical whenever the caller looks at them."""
 
     def __init__(self, n, weights_flat, games_per_rank, alpha, mode, seed=0, sync_every=64, ops=None, group=None,
-                 sync_impl="auto", first_slot=None, total_slots=None):
+                 sync_impl="auto", first_slot=None, total_slots=None, fused=True):
         self.ops = ops or CudaOps()
         self.group = group
         self.rank, self.world = rank_world(group)
@@ -170,13 +175,15 @@ class ShardedTrainer:
         total = self.world * self.B if total_slots is None else int(total_slots)
         self.trainer = self.ops.trainer(n, self.w, None, self.B, alpha, mode, seed, first_id=first, id_stride=total)
         self.since_sync = 0
-        self.syncs = 0
+        self.syncs = 0               # exchanges so far (= the epoch of the last one)
+        self.fused_syncs = 0         # ... of which inside a persistent training launch
+        self.fused = bool(fused) and self.sync_impl == "p2p"
 
     @property
     def launches(self):
-        """kernels of this package enqueued so far on this rank (trainer kernels + the sync kernels)"""
+        """kernels of this package enqueued so far on this rank (trainer kernels + the stand-alone sync kernels)"""
         per_sync = 1 if self.sync_impl == "p2p" else 2
-        return getattr(self.trainer, "launches", 0) + per_sync * self.syncs
+        return getattr(self.trainer, "launches", 0) + per_sync * (self.syncs - self.fused_syncs)
 
     @property
     def message_bytes(self):
@@ -205,6 +212,16 @@ class ShardedTrainer:
 
     def run(self, lock_steps, final_sync=False):
         done = 0
+        if self.sync_impl == "p2p" and self.fused and lock_steps > 0 and not (self.trainer.mode & cabi.RUN_STEPWISE):
+            # the whole call as ONE persistent launch per rank, the exchanges inside it
+            if self.ops.run_peers(self.trainer, lock_steps, self.peers, self.sync_every, self.since_sync, self.syncs + 1):
+                total = self.since_sync + lock_steps
+                self.syncs += total // self.sync_every
+                self.fused_syncs += total // self.sync_every
+                self.since_sync = total % self.sync_every
+                done = lock_steps
+            else:
+                self.fused = False
         while done < lock_steps:
             k = lock_steps - done
             if self.world > 1:

@@ -57,6 +57,8 @@ def parse():
     p.add_argument("--sync-every", type=int, default=128, help="lock-steps between weight syncs (N>1)")
     p.add_argument("--sync-impl", default="auto", choices=["auto", "p2p", "nccl"],
                    help="N>1 weight exchange: fused peer-memory kernel or NCCL allreduce + allgather")
+    p.add_argument("--no-fused", action="store_true",
+                   help="p2p exchange as a stand-alone kernel between persistent launches instead of inside them")
     p.add_argument("--boards", type=int, default=1 << 24, help="boards per GPU (sweep)")
     p.add_argument("--no-extras", action="store_true")
     p.add_argument("--no-configs", action="store_true", help="headline only: skip the `configs` object")
@@ -356,7 +358,8 @@ def td_bench(D, ctx, args, n, B, S, steps, warmup, mode, sync_every, first_slot,
     from game2048 import cabi, parallel
     w_host = torch.from_numpy(seeded_weights(n)).pin_memory()
     st = parallel.ShardedTrainer(n, w_host.numpy(), B, args.alpha, mode, seed=0, sync_every=sync_every,
-                                 sync_impl=args.sync_impl, first_slot=first_slot, total_slots=total_slots)
+                                 sync_impl=args.sync_impl, first_slot=first_slot, total_slots=total_slots,
+                                 fused=not args.no_fused)
     wd, games = st.w, st.trainer.games
     flush = ctx.zeros(64 << 20, torch.int32)                     # 256 MiB > 126 MB L2
     for _ in range(warmup):
@@ -450,7 +453,8 @@ def td_bench(D, ctx, args, n, B, S, steps, warmup, mode, sync_every, first_slot,
            "steps": steps, "warmup": warmup, "moves_per_sec": mv / (ms * 1e-3), "clocks": clocks, "e2e": e2e,
            "gpu_launches": int(launches_timed), "roofline": roof}
     if D.world > 1:
-        res.update(sync_check=bool(in_sync), sync_us=sync_us, sync_impl=st.sync_impl,
+        res.update(sync_check=bool(in_sync), sync_us=sync_us,
+                   sync_impl=st.sync_impl + (" (inside the persistent launch)" if st.fused else ""),
                    sync_message_bytes_per_rank=st.message_bytes,
                    sync_fallback_reason=getattr(st.ops, "peer_error", None))
     return res, st

@@ -303,6 +303,18 @@ typedef struct b2048_peers {
 } b2048_peers_t;
 int b2048_sync_peers(const b2048_peers_t *peers, int64_t count, uint32_t epoch, int max_ctas, b2048_stream_t stream);
 
+/* b2048_td_run with the exchange INSIDE the persistent launch: `steps` lock-steps in one cooperative kernel, and after
+ * every lock-step that completes a period of sync_every (since_sync = lock-steps already done in the current period, so
+ * the first sync comes after sync_every - since_sync lock-steps) all CTAs of every rank run the b2048_sync_peers exchange
+ * on the spot -- game state stays in registers, no relaunch and no separate sync kernel.  The syncs of the call use the
+ * epochs epoch, epoch + 1, ... (same numbering as b2048_sync_peers; the two may be mixed on one flag block).  Every rank
+ * must call with the same n, steps, sync_every, since_sync and epoch; weights must be peers->w[peers->rank].
+ * Returns B2048_ENOTSUP when the persistent kernel cannot be used (no cooperative launch, or the batch does not fit one
+ * wave): the caller then alternates b2048_td_run and b2048_sync_peers.  ATOMIC or DETERMINISTIC, SUM or MEAN. */
+int b2048_td_run_peers(int n, float *weights, const uint32_t *lut, const b2048_games_t *g, float alpha, int mode, int steps,
+                       uint64_t *upd_board, float *upd_dw, void *work, size_t work_bytes, const b2048_peers_t *peers,
+                       int sync_every, int since_sync, uint32_t epoch, b2048_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -138,6 +138,30 @@ def test_sync_forms_emulated_ranks_vs_oracle(eng, orc, fx, R, n, B):
             assert int(flags[k][cabi.PEER_FAULT].item()) == 0
     finish(w, ws, tr, "sync_peers")
 
+    # (d) the exchange inside the persistent training launch (b2048_td_run_peers): the 12 lock-steps of the schedule as
+    #     ONE launch per rank (syncs after lock-steps 5 and 10 inside it), then the stand-alone kernel for the last 2
+    w, ws, tr = fresh()
+    flags = [ctx.zeros(cabi.PEER_FLAG_WORDS, torch.int32) for _ in range(R)]
+    peers = []
+    for k in range(R):
+        p = cabi.Peers()
+        for q in range(R):
+            p.w[q], p.w_sync[q], p.flags[q] = w[q].data_ptr(), ws[q].data_ptr(), flags[q].data_ptr()
+        p.world, p.rank = R, k
+        peers.append(p)
+    torch.cuda.synchronize()
+    for k in range(R):
+        with torch.cuda.stream(streams[k]):
+            assert tr[k].run_peers(sum(periods), peers[k], periods[0], 0, 1)
+    torch.cuda.synchronize()
+    for k in range(R):
+        with torch.cuda.stream(streams[k]):
+            cabi.check(lib.b2048_sync_peers(C.byref(peers[k]), nw, 3, 16, engine.cur_stream()))
+    torch.cuda.synchronize()
+    for k in range(R):
+        assert int(flags[k][cabi.PEER_FAULT].item()) == 0
+    finish(w, ws, tr, "td_run_peers")
+
 
 def test_sync_peers_argument_errors_and_ragged_count(eng):
     """count not a multiple of 4 (scalar tail on the last rank), world 1 (a no-op exchange), bad arguments"""
