@@ -8,9 +8,10 @@ reproduce the 1-rank games exactly); only the final per-game statistics are gath
 Two implementations of the exchange (same formula; each leaves the replicas bit-identical):
   "p2p"   over NVLink / NVSwitch peer memory: the weights and w_sync of every rank are symmetric-memory allocations
           mapped into every process; rank r reduces slice r from remote loads and stores the result into every replica.
-          No NCCL call, no message buffers.  With `fused` (default) the exchange runs INSIDE the persistent training
-          launch (b2048_td_run_peers: run(S) is one kernel per rank however many syncs fall into it); otherwise, or
-          for a flush between launches, it is one stand-alone kernel per sync (b2048_sync_peers).
+          No NCCL call, no message buffers.  One stand-alone kernel per sync (b2048_sync_peers: 40 us at n=4 on
+          2 GPUs), or with `fused=True` INSIDE the persistent training launch (b2048_td_run_peers: run(S) is one kernel
+          per rank however many syncs fall into it; 28 us per sync, but that kernel variant runs its lock-steps 3 %
+          slower today, so it is not the default).
   "nccl"  b2048_delta_pack_bits -> allreduce(sum) of the float32 deltas + allgather of the one-bit-per-weight
           contributor planes (4.125 bytes per weight on the wire instead of the 8 of a float indicator) ->
           b2048_delta_apply_bits.  The portable path, and the one the CPU tier exercises under gloo.
@@ -34,6 +35,43 @@ def shard(total, world, rank):
     base, rem = divmod(int(total), int(world))
     first = rank * base + min(rank, rem)
     return first, base + (1 if rank < rem else 0)
+
+
+def symmetric_memory_ok(device):
+    """can torch map a (tiny) buffer of every rank into every process?  A collective: every rank must call it."""
+    try:
+        import torch.distributed._symmetric_memory as symm
+        t = symm.empty(64, dtype=torch.int32, device=device)
+        h = symm.rendezvous(t, dist.group.WORLD.group_name)
+        return len(h.buffer_ptrs) == dist.get_world_size()
+    except Exception:                                                 # noqa: BLE001
+        return False
+
+
+def init_distributed(local_rank, peer_exchange=True):
+    """torch.distributed over NCCL for this package's N > 1 paths: one process per GPU, NCCL for the plumbing
+    (barriers, the initial broadcast, 32-byte reductions of counters and timings).
+
+    Measured on B200 (profiles/r02_nccl_p2p_effect.txt): once NCCL has connected its NVLink P2P transport, every
+    GPU-scope fence of the persistent training kernel gets slower (26.8 -> 28.5 ms per 2,048 lock-steps, whether or
+    not a single NCCL collective runs in between), while peer mappings made through symmetric memory cost nothing.
+    The weight exchange of this package runs over NVLink in its own kernels (b2048_sync_peers), so NCCL's P2P
+    transport is switched off (NCCL_P2P_LEVEL=LOC: its few small collectives go through host shared memory) -- unless
+    symmetric memory is unavailable, in which case NCCL is re-initialised with P2P on and carries the exchange.
+    Returns {"p2p_exchange": bool, "nccl_p2p": bool}."""
+    import os
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    ours = peer_exchange and "NCCL_P2P_LEVEL" not in os.environ and "NCCL_P2P_DISABLE" not in os.environ
+    if ours:
+        os.environ["NCCL_P2P_LEVEL"] = "LOC"
+    dist.init_process_group("nccl", device_id=dev)
+    ok = symmetric_memory_ok(dev) if peer_exchange else False
+    if ours and not ok:
+        dist.destroy_process_group()
+        del os.environ["NCCL_P2P_LEVEL"]
+        dist.init_process_group("nccl", device_id=dev)
+    return {"p2p_exchange": bool(ok), "nccl_p2p": not (ours and ok)}
 
 
 def rank_world(group=None):
@@ -136,7 +174,7 @@ class ShardedTrainer:
     `final_sync` is set, so that the replicas are identical whenever the caller looks at them."""
 
     def __init__(self, n, weights_flat, games_per_rank, alpha, mode, seed=0, sync_every=64, ops=None, group=None,
-                 sync_impl="auto", first_slot=None, total_slots=None, fused=True):
+                 sync_impl="auto", first_slot=None, total_slots=None, fused=False):
         self.ops = ops or CudaOps()
         self.group = group
         self.rank, self.world = rank_world(group)

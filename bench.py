@@ -57,8 +57,8 @@ def parse():
     p.add_argument("--sync-every", type=int, default=128, help="lock-steps between weight syncs (N>1)")
     p.add_argument("--sync-impl", default="auto", choices=["auto", "p2p", "nccl"],
                    help="N>1 weight exchange: fused peer-memory kernel or NCCL allreduce + allgather")
-    p.add_argument("--no-fused", action="store_true",
-                   help="p2p exchange as a stand-alone kernel between persistent launches instead of inside them")
+    p.add_argument("--fused", action="store_true",
+                   help="p2p exchange inside the persistent launches (b2048_td_run_peers) instead of a kernel between them")
     p.add_argument("--boards", type=int, default=1 << 24, help="boards per GPU (sweep)")
     p.add_argument("--no-extras", action="store_true")
     p.add_argument("--no-configs", action="store_true", help="headline only: skip the `configs` object")
@@ -180,15 +180,18 @@ def bytes_per_update(n, evals_per_move):
 class Dist:
     """rank / world of this process and max / sum reductions over the ranks (device tensors, NCCL)"""
 
-    def __init__(self):
+    def __init__(self, sync_impl="auto"):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
         self.rank, self.world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
         self.local = int(os.environ.get("LOCAL_RANK", "0"))
         torch.cuda.set_device(self.local)
+        self.comm = None
         if self.world > 1 and not dist.is_initialized():
-            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+            importlib.import_module("2048_b200")
+            from game2048 import parallel
+            self.comm = parallel.init_distributed(self.local, peer_exchange=sync_impl != "nccl")
 
     def barrier(self):
         self.torch.cuda.synchronize()
@@ -359,7 +362,7 @@ def td_bench(D, ctx, args, n, B, S, steps, warmup, mode, sync_every, first_slot,
     w_host = torch.from_numpy(seeded_weights(n)).pin_memory()
     st = parallel.ShardedTrainer(n, w_host.numpy(), B, args.alpha, mode, seed=0, sync_every=sync_every,
                                  sync_impl=args.sync_impl, first_slot=first_slot, total_slots=total_slots,
-                                 fused=not args.no_fused)
+                                 fused=args.fused)
     wd, games = st.w, st.trainer.games
     flush = ctx.zeros(64 << 20, torch.int32)                     # 256 MiB > 126 MB L2
     for _ in range(warmup):
@@ -373,6 +376,7 @@ def td_bench(D, ctx, args, n, B, S, steps, warmup, mode, sync_every, first_slot,
     launches_timed = st.launches - l0
     c1 = games.read_counters()
     upd, mv, evals = c1["updates"] - c0["updates"], c1["moves"] - c0["moves"], c1["evals"] - c0["evals"]
+    print(f"[rank {D.rank}] n={n} B={B} S={S}: {ms / steps:.3f} ms/step, {upd} updates", file=sys.stderr, flush=True)
     mx, sm = D.max_sum([ms, float(upd), float(mv), float(evals)])
     ms, upd, mv, evals = mx[0], sm[1], sm[2], sm[3]
     value = upd / (ms * 1e-3)
@@ -455,13 +459,13 @@ def td_bench(D, ctx, args, n, B, S, steps, warmup, mode, sync_every, first_slot,
     if D.world > 1:
         res.update(sync_check=bool(in_sync), sync_us=sync_us,
                    sync_impl=st.sync_impl + (" (inside the persistent launch)" if st.fused else ""),
-                   sync_message_bytes_per_rank=st.message_bytes,
+                   sync_message_bytes_per_rank=st.message_bytes, comm=D.comm,
                    sync_fallback_reason=getattr(st.ops, "peer_error", None))
     return res, st
 
 
 def run_td(args):
-    D = Dist()
+    D = Dist(args.sync_impl)
     importlib.import_module("2048_b200")
     from game2048 import cabi, engine
     ctx = engine.Context.get()
@@ -490,7 +494,7 @@ def run_td(args):
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(args)}
         for k in ("moves_per_sec", "clocks", "e2e", "gpu_launches", "roofline", "sync_check", "sync_us", "sync_impl",
-                  "sync_message_bytes_per_rank", "sync_fallback_reason"):
+                  "sync_message_bytes_per_rank", "sync_fallback_reason", "comm"):
             if k in res:
                 line[k] = res[k]
         line["cpu_baseline"] = cpu
