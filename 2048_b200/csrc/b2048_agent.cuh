@@ -1479,7 +1479,11 @@ constexpr int PERSIST_TILE = 32;           // FAST path: at most this many slots
 // registers across the barrier and applies / flushes them itself: no lists, no cursors, no global round trip
 // except the weight gathers and the atomics.  Otherwise slots are processed in rounds through the b2048_td_step
 // staging arrays and per-CTA key lists in global memory.
-template <int N, bool EXACT, bool MEAN, bool DIRECT, bool FAST, bool PEERS>
+// SCAN (n <= 5, chosen by the launcher when a lock-step makes at least half as many contributions as there are weights):
+// no first-touch bookkeeping at all.  Phase B fires non-returning REDs (1.5 instead of 2.3 LSU cycles per lane), and the
+// apply phase is a dense, coalesced scan of the accumulators by all CTAs (8.9 MB at n = 4: ~60 KB per SM and lock-step),
+// which finds the touched keys by their non-zero contributor count.
+template <int N, bool EXACT, bool MEAN, bool DIRECT, bool FAST, bool PEERS, bool SCAN>
 __global__ void __launch_bounds__(PERSIST_THREADS, 1)
 td_persist_kernel(PersistBuffers pb, PersistCtrl *ctrl, const uint32_t *__restrict__ lut, b2048_games_t g, float alpha,
                   int steps, uint64_t *upd_board, float *upd_dw, int spc, long long *tlog, const __grid_constant__ PeerSync ps)
@@ -1645,7 +1649,12 @@ td_persist_kernel(PersistBuffers pb, PersistCtrl *ctrl, const uint32_t *__restri
                         if (pb.delta) atomicAdd(pb.delta + k, d);
                     } else if (EXACT) {
                         atomicAdd(accq + k, (unsigned long long)qd);
-                        if (ld) oldu[s] = atomicAdd(pb.cnt + k, 1u);
+                        if (ld) {
+                            if (SCAN) atomicAdd(pb.cnt + k, 1u);
+                            else oldu[s] = atomicAdd(pb.cnt + k, 1u);
+                        }
+                    } else if (SCAN) {
+                        atomicAdd(acc2 + k, make_float2(d, ld ? 1.0f : 0.0f));     // result unused: RED
                     } else if (ld) {
                         oldf[s] = atomicAdd(acc2 + k, make_float2(d, 1.0f)).y;
                     } else {
@@ -1658,7 +1667,7 @@ td_persist_kernel(PersistBuffers pb, PersistCtrl *ctrl, const uint32_t *__restri
             for (int s = 0; s < 8; s++) dirty |= uint32_t(oldc[s] == 0u) << s;
             if (!FAST) {
                 first = 0;
-                if (!DIRECT) {
+                if (!DIRECT && !SCAN) {
 #pragma unroll
                     for (int s = 0; s < 8; s++) first |= uint32_t(EXACT ? (oldu[s] == 0u) : (oldf[s] == 0.0f)) << s;
                 }
@@ -1740,14 +1749,16 @@ td_persist_kernel(PersistBuffers pb, PersistCtrl *ctrl, const uint32_t *__restri
         float hw = 0.0f, hd = 0.0f, wv[8], dv[8];
         if (FAST && !DIRECT) {
             first = 0;
+            if (!SCAN) {
 #pragma unroll
-            for (int s = 0; s < 8; s++) first |= uint32_t(EXACT ? (oldu[s] == 0u) : (oldf[s] == 0.0f)) << s;
+                for (int s = 0; s < 8; s++) first |= uint32_t(EXACT ? (oldu[s] == 0u) : (oldf[s] == 0.0f)) << s;
 #pragma unroll
-            for (int s = 0; s < 8; s++)
-                if ((first >> s) & 1u) {
-                    wv[s] = __ldcg(pb.w + key_off + idx[s]);
-                    if (pb.delta) dv[s] = __ldcg(pb.delta + key_off + idx[s]);
-                }
+                for (int s = 0; s < 8; s++)
+                    if ((first >> s) & 1u) {
+                        wv[s] = __ldcg(pb.w + key_off + idx[s]);
+                        if (pb.delta) dv[s] = __ldcg(pb.delta + key_off + idx[s]);
+                    }
+            }
             if (hot_on) {
                 hw = __ldcg(pb.w + hk);
                 if (pb.delta) hd = __ldcg(pb.delta + hk);
@@ -1763,7 +1774,61 @@ td_persist_kernel(PersistBuffers pb, PersistCtrl *ctrl, const uint32_t *__restri
                 if (EXACT) { hqv = __ldcg(hotq + hq); hcv = __ldcg(hotc + hq); }
                 else hv = __ldcg(hot2 + hq);
             }
-            if (FAST) {
+            if (SCAN) {
+                // dense scan of the accumulators, 4 x 16 bytes per thread in flight; a key is touched iff its contributor
+                // count is non-zero (float modes: the .y of its {sum, count} pair; exact modes: cnt[k])
+                constexpr int64_t NWT = table_offset(N, F);
+                constexpr int SB = 4;
+                const int64_t gsz = int64_t(gridDim.x) * blockDim.x, g0 = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+                if (EXACT) {
+                    static_assert(NWT % 4 == 0, "cnt is scanned four keys at a time");
+                    const uint4 *c4 = reinterpret_cast<const uint4 *>(pb.cnt);
+                    for (int64_t q0 = g0; q0 < NWT / 4; q0 += SB * gsz) {
+                        uint4 cv[SB];
+#pragma unroll
+                        for (int a = 0; a < SB; a++) {
+                            const int64_t q = q0 + a * gsz;
+                            cv[a] = q < NWT / 4 ? __ldcg(c4 + q) : make_uint4(0u, 0u, 0u, 0u);
+                        }
+#pragma unroll
+                        for (int a = 0; a < SB; a++) {
+                            const uint32_t cc[4] = {cv[a].x, cv[a].y, cv[a].z, cv[a].w};
+#pragma unroll
+                            for (int e = 0; e < 4; e++)
+                                if (cc[e]) {
+                                    const uint32_t k = uint32_t(4 * (q0 + a * gsz) + e);
+                                    const float u = update_value<true, MEAN>((long long)__ldcg(accq + k), 0.0f, float(cc[e]));
+                                    __stcg(accq + k, 0ULL);
+                                    __stcg(pb.cnt + k, 0u);
+                                    add_weight(pb.w, pb.delta, k, u);
+                                }
+                        }
+                    }
+                } else {
+                    static_assert(NWT % 2 == 0, "the {sum, count} pairs are scanned two keys at a time");
+                    const float4 *a4 = reinterpret_cast<const float4 *>(pb.acc);
+                    for (int64_t q0 = g0; q0 < NWT / 2; q0 += SB * gsz) {
+                        float4 v[SB];
+#pragma unroll
+                        for (int a = 0; a < SB; a++) {
+                            const int64_t q = q0 + a * gsz;
+                            v[a] = q < NWT / 2 ? __ldcg(a4 + q) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                        }
+#pragma unroll
+                        for (int a = 0; a < SB; a++) {
+                            const uint32_t k = uint32_t(2 * (q0 + a * gsz));
+                            if (v[a].y != 0.0f) {
+                                __stcg(acc2 + k, make_float2(0.0f, 0.0f));
+                                add_weight(pb.w, pb.delta, k, update_value<false, MEAN>(0, v[a].x, v[a].y));
+                            }
+                            if (v[a].w != 0.0f) {
+                                __stcg(acc2 + k + 1, make_float2(0.0f, 0.0f));
+                                add_weight(pb.w, pb.delta, k + 1, update_value<false, MEAN>(0, v[a].z, v[a].w));
+                            }
+                        }
+                    }
+                }
+            } else if (FAST) {
                 // the keys this thread touched first (registers): every accumulator load first, then the arithmetic
                 // and the stores -- one L2 round trip for up to 8 keys instead of one per key
                 float2 av[8];
@@ -1963,10 +2028,10 @@ int td_update_impl(float *weights, float *delta, const uint64_t *boards, const f
 }
 
 // ---- persistent trainer launch ---------------------------------------------------------------------
-template <int N, bool EXACT, bool MEAN, bool DIRECT, bool FAST, bool PEERS>
+template <int N, bool EXACT, bool MEAN, bool DIRECT, bool FAST, bool PEERS, bool SCAN>
 int launch_persist(int grid, cudaStream_t st, void **args)
 {
-    auto kern = td_persist_kernel<N, EXACT, MEAN, DIRECT, FAST, PEERS>;
+    auto kern = td_persist_kernel<N, EXACT, MEAN, DIRECT, FAST, PEERS, SCAN>;
     const int smem = small_count(N) * (EXACT ? 14 : 10);           // sums, counts, dirty list
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);   // per call: no cache
     if (e != cudaSuccess) return int(e);
@@ -1983,13 +2048,30 @@ int launch_persist(int grid, cudaStream_t st, void **args)
     return e == cudaSuccess ? 0 : int(e);
 }
 
-template <int N, bool FAST, bool PEERS>
+// instantiated combinations: the in-launch exchange (PEERS) exists for the per-key-mean rule only, the scanning apply
+// (SCAN) for n <= 5 and never for the direct mode (which has no apply phase)
+template <int N, bool FAST, bool PEERS, bool SCAN>
 int launch_persist_mode(bool det, bool mean, int grid, cudaStream_t st, void **args)
 {
-    if (!det && !mean) return launch_persist<N, false, false, true, FAST, PEERS>(grid, st, args);
-    if (!det) return launch_persist<N, false, true, false, FAST, PEERS>(grid, st, args);
-    if (mean) return launch_persist<N, true, true, false, FAST, PEERS>(grid, st, args);
-    return launch_persist<N, true, false, false, FAST, PEERS>(grid, st, args);
+    if constexpr (PEERS) {
+        if (!mean) return B2048_ENOTSUP;
+        if (!det) return launch_persist<N, false, true, false, FAST, true, SCAN>(grid, st, args);
+        return launch_persist<N, true, true, false, FAST, true, SCAN>(grid, st, args);
+    } else {
+        if (!det && !mean) return launch_persist<N, false, false, true, FAST, false, false>(grid, st, args);
+        if (!det) return launch_persist<N, false, true, false, FAST, false, SCAN>(grid, st, args);
+        if (mean) return launch_persist<N, true, true, false, FAST, false, SCAN>(grid, st, args);
+        return launch_persist<N, true, false, false, FAST, false, SCAN>(grid, st, args);
+    }
+}
+
+template <int N, bool FAST, bool PEERS>
+int launch_persist_scan(bool scan, bool det, bool mean, int grid, cudaStream_t st, void **args)
+{
+    if constexpr (N <= 5) {
+        if (scan) return launch_persist_mode<N, FAST, PEERS, true>(det, mean, grid, st, args);
+    }
+    return launch_persist_mode<N, FAST, PEERS, false>(det, mean, grid, st, args);
 }
 
 template <int N>
@@ -2027,10 +2109,15 @@ int td_run_persistent(float *weights, float *delta, const uint32_t *lut, const b
     // FAST: one phase-B round per lock-step, state in registers, staging and key list in shared memory
     const bool fast = spc <= PERSIST_THREADS / num_feat(N) && spc <= PERSIST_TILE && !(mode & B2048_RUN_GENERIC);
     const bool with_peers = ps.sync_every > 0;
-    const int rc = fast ? (with_peers ? launch_persist_mode<N, true, true>(det, mean, grid, st, args)
-                                      : launch_persist_mode<N, true, false>(det, mean, grid, st, args))
-                        : (with_peers ? launch_persist_mode<N, false, true>(det, mean, grid, st, args)
-                                      : launch_persist_mode<N, false, false>(det, mean, grid, st, args));
+    // scanning apply: when a lock-step makes at least half as many contributions (8 F per slot) as there are weights
+    // (n = 4 from 4,096 games, n = 5 from 15,800), or when forced either way (parity tests run both)
+    bool scan = N <= 5 && B * 8 * num_feat(N) * 2 >= L.nw;
+    if (mode & B2048_RUN_SCAN) scan = N <= 5;
+    if (mode & B2048_RUN_LISTS) scan = false;
+    const int rc = fast ? (with_peers ? launch_persist_scan<N, true, true>(scan, det, mean, grid, st, args)
+                                      : launch_persist_scan<N, true, false>(scan, det, mean, grid, st, args))
+                        : (with_peers ? launch_persist_scan<N, false, true>(scan, det, mean, grid, st, args)
+                                      : launch_persist_scan<N, false, false>(scan, det, mean, grid, st, args));
 #ifdef B2048_PERSIST_TLOG
     if (tlog) {
         std::vector<long long> h(size_t(grid) * 16 * 8);

@@ -14,6 +14,7 @@ namespace {
 using namespace b2048;
 
 constexpr unsigned FULL = 0xFFFFFFFFu;
+constexpr int B2048_RUN_LAYOUT = B2048_RUN_GENERIC | B2048_RUN_SCAN | B2048_RUN_LISTS;   // layout hints of b2048_td_run
 
 inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -634,11 +634,11 @@ int b2048_td_run(int n, float *weights, float *delta, const uint32_t *lut, const
                  int mode, int steps, uint64_t *upd_board, float *upd_dw, void *work, size_t work_bytes,
                  b2048_stream_t stream)
 {
-    if (steps < 0 || (mode & ~(7 | B2048_RUN_STEPWISE | B2048_RUN_GENERIC))) return B2048_EINVAL;
+    if (steps < 0 || (mode & ~(7 | B2048_RUN_STEPWISE | B2048_RUN_LAYOUT))) return B2048_EINVAL;
     if (!games_ok(g) || num_feat(n) < 0 || !weights || !lut || !upd_board || !upd_dw) return B2048_EINVAL;
     if (steps == 0 || g->B == 0) return 0;
     const bool stepwise = mode & (B2048_RUN_STEPWISE | B2048_UPD_SORTED);
-    const int layout = mode & B2048_RUN_GENERIC;
+    const int layout = mode & B2048_RUN_LAYOUT;
     mode &= 7;
     if (!stepwise && cooperative_ok()) {
         int rc = agent_ops(n)->td_run_persistent(weights, delta, lut, g, alpha, mode | layout, steps, upd_board, upd_dw, work,
@@ -657,7 +657,7 @@ int b2048_td_run_peers(int n, float *weights, const uint32_t *lut, const b2048_g
                        uint64_t *upd_board, float *upd_dw, void *work, size_t work_bytes, const b2048_peers_t *peers,
                        int sync_every, int since_sync, uint32_t epoch, b2048_stream_t stream)
 {
-    if (steps < 0 || (mode & ~(7 | B2048_RUN_GENERIC)) || (mode & B2048_UPD_SORTED)) return B2048_EINVAL;
+    if (steps < 0 || (mode & ~(7 | B2048_RUN_LAYOUT)) || (mode & B2048_UPD_SORTED)) return B2048_EINVAL;
     if (!games_ok(g) || num_feat(n) < 0 || !weights || !lut || !upd_board || !upd_dw) return B2048_EINVAL;
     if (!peers || peers->world < 1 || peers->world > B2048_MAX_PEERS || peers->rank < 0 || peers->rank >= peers->world ||
         sync_every < 1 || since_sync < 0 || since_sync >= sync_every || epoch == 0)
@@ -679,7 +679,7 @@ int b2048_td_run_peers(int n, float *weights, const uint32_t *lut, const b2048_g
 
 int64_t b2048_td_run_launches(int n, int64_t B, int mode, int steps)
 {
-    if (num_feat(n) < 0 || B < 0 || steps < 0 || (mode & ~(7 | B2048_RUN_STEPWISE | B2048_RUN_GENERIC))) return -1;
+    if (num_feat(n) < 0 || B < 0 || steps < 0 || (mode & ~(7 | B2048_RUN_STEPWISE | B2048_RUN_LAYOUT))) return -1;
     if (B == 0 || steps == 0) return 0;
     const bool stepwise = mode & (B2048_RUN_STEPWISE | B2048_UPD_SORTED);
     if (!stepwise && cooperative_ok()) return 1;                   // the persistent kernel

@@ -247,6 +247,11 @@ int b2048_td_phase_a(int n, const float *weights, const uint32_t *lut, const b20
 /* mode | B2048_RUN_GENERIC: the persistent kernel in its generic slot layout (rounds over the staging arrays and per-CTA
  * key lists) even where the one-round register layout would fit; same results, used by the parity tests */
 #define B2048_RUN_GENERIC 16
+/* the apply phase of the persistent kernel: a dense scan of the accumulators (default when a lock-step makes at least
+ * half as many contributions as there are weights; n <= 5) or the lists of first-touched keys.  mode | B2048_RUN_SCAN /
+ * B2048_RUN_LISTS force one of them (same results; the parity tests run both). */
+#define B2048_RUN_SCAN 32
+#define B2048_RUN_LISTS 64
 /* number of kernel launches b2048_td_run(n, B slots, mode, steps) enqueues on this device (1 = persistent) */
 int64_t b2048_td_run_launches(int n, int64_t B, int mode, int steps);
 int b2048_td_run(int n, float *weights, float *delta, const uint32_t *lut, const b2048_games_t *g, float alpha,

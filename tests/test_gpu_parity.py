@@ -423,14 +423,19 @@ def test_td_lockstep_deterministic_bit_exact(eng, orc, fx, n, B):
                                              # BASELINE configs[2] shapes: n=5 with 65,536 games on 1 / 2 GPUs
                                              (5, 32768, 12, None), (5, 65536, 8, None),
                                              # n=6 in the generic layout (more slots per CTA than one round; forced)
-                                             (6, 4096, 12, None), (6, 300, 40, "generic")])
+                                             (6, 4096, 12, None), (6, 300, 40, "generic"),
+                                             # both apply phases forced where the launcher would pick the other one
+                                             (4, 4096, 40, "lists"), (4, 1000, 80, "scan"), (4, 64, 100, "generic+scan"),
+                                             (5, 6000, 30, "scan"), (3, 2000, 40, "scan"), (2, 500, 60, "scan")])
 def test_td_persistent_paths_bit_exact(eng, orc, fx, monkeypatch, n, B, steps, force):
     """b2048_td_run's persistent kernel gives the oracle's bits in the deterministic modes in both slot layouts:
     one phase-B round per CTA with the state in registers ((6, 700), (4, 3000), (3, 1000), (2, 2000), (4, 8)), and
     the generic layout (rounds over global staging and key lists: forced with B2048_RUN_GENERIC, or the larger
     shapes, among them n=5 at 32,768 / 65,536 games and n=6 at 4,096)."""
     ctx, engine, cabi = eng
-    layout = cabi.RUN_GENERIC if force == "generic" else 0
+    layout = 0
+    for word in (force or "").split("+"):
+        layout |= {"": 0, "generic": cabi.RUN_GENERIC, "scan": cabi.RUN_SCAN, "lists": cabi.RUN_LISTS}[word]
     for rule, mode, alpha in ((4, cabi.UPD_DETERMINISTIC | cabi.UPD_MEAN, 0.25),
                               (3, cabi.UPD_DETERMINISTIC | cabi.UPD_SUM, 0.25 / B)):
         w0 = fx.flat(fx.init_weights32(n, 41)).astype(np.float32)
@@ -572,7 +577,7 @@ def test_argument_errors(eng):
     tr = engine.TDTrainer(ctx, 4, w, games, 0.25, cabi.UPD_ATOMIC | cabi.UPD_MEAN)
     assert L.b2048_td_run(4, engine.dptr(w), None, engine.dptr(ctx.lut), C.byref(games.c), C.c_float(0.25), 2, 5,
                           engine.dptr(tr.upd_board), engine.dptr(tr.upd_dw), None, 0, None) == -3   # no workspace
-    assert L.b2048_td_run(4, engine.dptr(w), None, engine.dptr(ctx.lut), C.byref(games.c), C.c_float(0.25), 32, 5,
+    assert L.b2048_td_run(4, engine.dptr(w), None, engine.dptr(ctx.lut), C.byref(games.c), C.c_float(0.25), 128, 5,
                           engine.dptr(tr.upd_board), engine.dptr(tr.upd_dw), engine.dptr(tr.work), tr.work.numel(),
                           None) == -1                                                               # unknown mode bit
     # look-ahead entry points
