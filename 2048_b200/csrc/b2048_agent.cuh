@@ -1479,7 +1479,7 @@ constexpr int PERSIST_TILE = 32;           // FAST path: at most this many slots
 // registers across the barrier and applies / flushes them itself: no lists, no cursors, no global round trip
 // except the weight gathers and the atomics.  Otherwise slots are processed in rounds through the b2048_td_step
 // staging arrays and per-CTA key lists in global memory.
-// SCAN (n <= 5, chosen by the launcher when a lock-step makes at least half as many contributions as there are weights):
+// SCAN (n <= 5; the launcher's choice for the float modes in the generic layout):
 // no first-touch bookkeeping at all.  Phase B fires non-returning REDs (1.5 instead of 2.3 LSU cycles per lane), and the
 // apply phase is a dense, coalesced scan of the accumulators by all CTAs (8.9 MB at n = 4: ~60 KB per SM and lock-step),
 // which finds the touched keys by their non-zero contributor count.
@@ -2106,12 +2106,13 @@ int td_run_persistent(float *weights, float *delta, const uint32_t *lut, const b
     PeerSync ps{};                                                 // sync_every = 0: single GPU
     if (peer_sync) ps = *peer_sync;
     void *args[] = {&pb, &ctrl, &lut, &games, &alpha, &steps, &upd_board, &upd_dw, &spc_i, &tlog, &ps};
+    const bool with_peers = ps.sync_every > 0;
     // FAST: one phase-B round per lock-step, state in registers, staging and key list in shared memory
     const bool fast = spc <= PERSIST_THREADS / num_feat(N) && spc <= PERSIST_TILE && !(mode & B2048_RUN_GENERIC);
-    const bool with_peers = ps.sync_every > 0;
-    // scanning apply: when a lock-step makes at least half as many contributions (8 F per slot) as there are weights
-    // (n = 4 from 4,096 games, n = 5 from 15,800), or when forced either way (parity tests run both)
-    bool scan = N <= 5 && B * 8 * num_feat(N) * 2 >= L.nw;
+    // scanning apply: float modes in the generic layout (measured, profiles/r02_td_scan_vs_lists.txt: 11-49 % faster there;
+    // the one-round register layout keeps its lists, 5 % faster at 4,096 games; exact modes: the two-array scan loses
+    // 4-8 %), or when forced either way (the parity tests run both)
+    bool scan = N <= 5 && !det && !fast;
     if (mode & B2048_RUN_SCAN) scan = N <= 5;
     if (mode & B2048_RUN_LISTS) scan = false;
     const int rc = fast ? (with_peers ? launch_persist_scan<N, true, true>(scan, det, mean, grid, st, args)

@@ -18,14 +18,20 @@ p.add_argument("--sorted", action="store_true")
 p.add_argument("--warm", type=int, default=600)
 p.add_argument("--steps", type=int, default=100)
 p.add_argument("--split", action="store_true", help="time phase A / phase B separately with events")
+p.add_argument("--layout", default="", help="force persistent-kernel variants: generic, scan, lists ('+'-joined)")
+p.add_argument("--so", default="", help="load this libb2048.so instead of the in-tree one (lab builds)")
 a = p.parse_args()
 import torch
 importlib.import_module("2048_b200")
 from game2048 import cabi, engine
+if a.so:
+    cabi.SO_PATH = os.path.abspath(a.so)
 import bench
 ctx = engine.Context.get()
 mode = (cabi.UPD_DETERMINISTIC if a.mode == "deterministic" else 0) | (cabi.UPD_MEAN if a.rule == "mean" else 0) | \
        (cabi.UPD_SORTED if a.sorted else 0)
+for word in a.layout.split("+"):
+    mode |= {"": 0, "generic": cabi.RUN_GENERIC, "scan": cabi.RUN_SCAN, "lists": cabi.RUN_LISTS}[word]
 wd = ctx.to_device(bench.seeded_weights(a.n))
 games = engine.GameBatch(a.games, seed=0, ctx=ctx).init()
 tr = engine.TDTrainer(ctx, a.n, wd, games, 0.25 if a.rule == "mean" else 0.25 / a.games, mode)
@@ -45,4 +51,5 @@ else:
     torch.cuda.synchronize()
     ms = e[0].elapsed_time(e[1])
     c1 = games.read_counters()
-    print(f"{a.steps} lock-steps: {ms / a.steps * 1e3:.2f} us each, {(c1['updates'] - c0['updates']) / ms / 1e3:.1f} M updates/s")
+    print(f"n={a.n} games={a.games} {a.mode} {a.rule} {a.layout or 'default'}: {a.steps} lock-steps: {ms / a.steps * 1e3:.2f} us each, "
+          f"{(c1['updates'] - c0['updates']) / ms / 1e3:.1f} M updates/s")
