@@ -568,7 +568,9 @@ greedy_play_kernel(const float *__restrict__ w, const uint32_t *__restrict__ lut
                 } else {
                     odo++;
                     Philox4 r = spawn_words(g.seed, id, odo, 0u);
-                    sp = spawn_apply(board, r.x, r.y);
+                    sp = 0;
+                    if (trace_spawn) sp = spawn_apply(board, r.x, r.y);
+                    else spawn_apply_nonempty(board, r.x, r.y);       // the search-free form (no record wanted)
                 }
                 if (d == 0 && trace_spawn && int64_t(odo) <= trace_len) trace_spawn[slot * trace_len + odo - 1] = uint16_t(sp);
                 steps_done++;
@@ -576,6 +578,274 @@ greedy_play_kernel(const float *__restrict__ w, const uint32_t *__restrict__ lut
         }
     }
     if (in && d == 0) {                                             // the game the group still holds
+        g.board[slot] = board;
+        g.score[slot] = score;
+        g.moves[slot] = odo;
+        g.flags[slot] = uint8_t(flags);
+        if (!(flags & B2048_F_DONE)) c_active++;
+    }
+    warp_add_counter(g.counters + B2048_CTR_MOVES, c_moves);
+    warp_add_counter(g.counters + B2048_CTR_EVALS, c_evals);
+    warp_add_counter(g.counters + B2048_CTR_FINISHED, c_fin);
+    warp_add_counter(g.counters + B2048_CTR_SCORE_SUM, c_score);
+    warp_add_counter(g.counters + B2048_CTR_MOVES_SUM, c_msum);
+    warp_add_counter(g.counters + B2048_CTR_OVERFLOW, c_ovf);
+    warp_add_counter(g.counters + B2048_CTR_ACTIVE, c_active);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Small batches (BASELINE configs[0]: 1,000 games): greedy play is then bound by the LATENCY of one move -- LUT move,
+// table indices, one L2 round trip for the gather, argmax, spawn -- times the length of the longest game, with most
+// of the chip idle.  This kernel spends the idle lanes on looking one move ahead:
+//   * 16 lanes per game, lane = (d, e) = (direction of this move, direction of the next one);
+//   * the spawn after a move depends only on the afterstate and on Philox words keyed by (game id, move number), so
+//     for each of the four candidate afterstates a_d the board b_d = spawn(a_d) of the NEXT move is known before any
+//     value is: lane (d, e) computes a_d, b_d, and the second-level afterstate a_de = move(b_d, e);
+//   * the gathers of all 4 + 16 afterstates are issued together: ONE L2 round trip decides TWO moves
+//     (argmax over d among the lanes (d, 0), then over e inside the winning group);
+//   * the Philox words of the following two moves are computed in the shadow of the gathers;
+//   * the row LUT sits in shared memory (128 KB of lines + 64 KB of merge codes, staged once per CTA).
+// The decisions, sums (table order) and tie rules are those of greedy_play_kernel move for move, so the games are
+// bit-identical; 5x the gather traffic is what the otherwise idle L2 pays for halving the latency per move.
+// No replay / trace support: the launcher takes greedy_play_kernel for those.
+// ------------------------------------------------------------------------------------------------
+struct LutShared {
+    const uint16_t *row;
+    const uint8_t *code;
+    // the entry in b2048_lut_build's format, rebuilt from the two shared-memory tables
+    __device__ __forceinline__ uint32_t operator()(uint32_t line) const
+    {
+        const uint32_t r = row[line], c = code[line];
+        uint32_t t = c & (c >> 1);
+        t &= t >> 2;                                       // bit 0 / 4: that merge exponent is 15 (a 2^16 would appear)
+        const uint32_t ovf = (t & 0x11u) ? 1u : 0u;
+        return r | (c << 16) | (uint32_t((r != line) | ovf) << 24) | (ovf << 25);
+    }
+};
+
+constexpr int LUT_SMEM_BYTES = 65536 * 2 + 65536;
+
+__device__ __forceinline__ void stage_lut_shared(const uint32_t *__restrict__ lut, unsigned char *smem)
+{
+    uint16_t *srow = reinterpret_cast<uint16_t *>(smem);
+    uint8_t *scode = smem + 65536 * 2;
+    for (int q = threadIdx.x; q < 65536 / 4; q += blockDim.x) {
+        const uint4 e = __ldg(reinterpret_cast<const uint4 *>(lut) + q);
+        reinterpret_cast<uint2 *>(srow)[q] = make_uint2((e.x & 0xFFFFu) | (e.y << 16), (e.z & 0xFFFFu) | (e.w << 16));
+        reinterpret_cast<uint32_t *>(scode)[q] = ((e.x >> 16) & 0xFFu) | (((e.y >> 16) & 0xFFu) << 8) |
+                                                 (((e.z >> 16) & 0xFFu) << 16) | (((e.w >> 16) & 0xFFu) << 24);
+    }
+    __syncthreads();
+}
+
+// slide+merge in direction d from the two shared-memory tables: the afterstate, whether it differs from the board, and
+// the four merge-code bytes of its lines (spec_gain / spec_overflow decode them later, off the critical path)
+__device__ __forceinline__ uint64_t spec_move(const uint16_t *__restrict__ srow, const uint8_t *__restrict__ scode,
+                                              uint64_t b, int d, uint32_t &codes)
+{
+    uint64_t x = (d & 1) ? transpose(b) : b;
+    if (d & 2) x = flip_h(x);
+    uint64_t out = 0;
+    codes = 0;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const uint32_t line = uint32_t(x >> (48 - 16 * r)) & 0xFFFFu;
+        out |= uint64_t(srow[line]) << (48 - 16 * r);
+        codes |= uint32_t(scode[line]) << (8 * r);
+    }
+    if (d & 2) out = flip_h(out);
+    return (d & 1) ? transpose(out) : out;
+}
+
+__device__ __forceinline__ bool spec_overflow(uint32_t codes)        // some merge exponent is 15: a 2^16 would appear
+{
+    uint32_t t = codes & (codes >> 1);
+    t &= t >> 2;
+    return (t & 0x11111111u) != 0;
+}
+
+__device__ __forceinline__ uint32_t spec_gain(uint32_t codes)        // score += 2^(x+1) per merge (game_logic.py:33)
+{
+    uint32_t sc = 0;
+#pragma unroll
+    for (int q = 0; q < 8; q++) sc += (2u << ((codes >> (4 * q)) & 15u)) & ~2u;
+    return sc;
+}
+
+constexpr int SPEC_THREADS = 128;
+
+template <int N>
+__global__ void __launch_bounds__(SPEC_THREADS, 1)
+greedy_spec_kernel(const float *__restrict__ w, const uint32_t *__restrict__ lut, b2048_games_t g, int max_steps,
+                   int limit_tile, int step_limit)
+{
+    constexpr int F = num_feat(N);
+    extern __shared__ __align__(16) unsigned char lut_smem[];
+    stage_lut_shared(lut, lut_smem);
+    const LutShared L{reinterpret_cast<const uint16_t *>(lut_smem), lut_smem + 65536 * 2};
+    const int lane = threadIdx.x & 31, hl = lane & 15, d = hl >> 2, e = hl & 3;
+    const int gbase = lane & 16;                                    // first lane of this game's half-warp
+    unsigned long long *queue = reinterpret_cast<unsigned long long *>(g.counters + B2048_CTR_QUEUE);
+    int64_t slot = -1;
+    uint64_t board = 0, id = 0;
+    uint32_t score = 0, odo = 0, flags = B2048_F_DONE;
+    bool in = false, run = false, more = true;
+    int steps_done = 0;
+    Philox4 p1{}, p2{};                                             // spawn words of moves odo + 1, odo + 2
+    uint32_t c_moves = 0, c_evals = 0, c_fin = 0, c_score = 0, c_msum = 0, c_ovf = 0, c_active = 0;
+    while (true) {
+        while (more && !(run && steps_done < max_steps)) {
+            if (in && hl == 0) {
+                g.board[slot] = board;
+                g.score[slot] = score;
+                g.moves[slot] = odo;
+                g.flags[slot] = uint8_t(flags);
+                if (!(flags & B2048_F_DONE)) c_active++;
+            }
+            unsigned long long nx = 0;
+            if (hl == 0) nx = atomicAdd(queue, 1ULL);
+            nx = (unsigned long long)__shfl_sync(0xFFFFu << gbase, (long long)nx, gbase);
+            slot = int64_t(nx);
+            in = slot < g.B;
+            more = in;
+            board = in ? g.board[slot] : 0;
+            score = in ? g.score[slot] : 0;
+            odo = in ? g.moves[slot] : 0;
+            flags = in ? g.flags[slot] : B2048_F_DONE;
+            id = in ? g.game_id[slot] : 0;
+            run = in && !(flags & B2048_F_DONE);
+            steps_done = 0;
+            if (in && !run) in = false;
+            if (run) {
+                p1 = spawn_words(g.seed, id, odo + 1u, 0u);
+                p2 = spawn_words(g.seed, id, odo + 2u, 0u);
+            }
+        }
+        const bool go = run && steps_done < max_steps;
+        if (!__any_sync(FULL, go)) break;
+        run = go;
+        // "game over" is not tested up front: a board is over iff no direction changes it, i.e. iff the argmax below
+        // finds no candidate -- the same for the board after the first move and its second-level moves
+        const bool limit_hit = run && ((limit_tile && max_tile(board) >= limit_tile) || int(odo) >= step_limit);
+        // ---- first level (everything below up to the commits is executed by all 32 lanes: shuffles inside).  The order
+        //      of the code is the order of issue: the first-level gathers leave before the second level is even computed,
+        //      and the first-level argmax runs while the second-level gathers are in flight.
+        uint32_t codes1 = 0, codes2 = 0;
+        const uint64_t a1 = spec_move(L.row, L.code, board, d, codes1);
+        const bool valid1 = run && !limit_hit && (a1 != board || spec_overflow(codes1));
+        const bool need1 = valid1 && e == 0;                           // lane (d, 0) scores a_d
+        uint32_t idx1[F];
+        feature_indices<N>(a1, idx1);
+        float v1[F];
+        for_each_feature<N>([&](auto I) {
+            constexpr int i = decltype(I)::value;
+            v1[i] = need1 ? __ldg(w + table_offset(N, i) + idx1[i]) : 0.0f;
+        });
+        // ---- second level: the board after the spawn that WOULD follow a_d, and its move in direction e
+        const bool ovf1 = spec_overflow(codes1);
+        uint64_t b1 = a1;
+        if (valid1 && !ovf1) spawn_apply_nonempty(b1, p1.x, p1.y);
+        // the second move exists only if the first one is legal, the game may go on after it and this launch may play it
+        const bool stop2 = !valid1 || ovf1 || (limit_tile && max_tile(b1) >= limit_tile) ||
+                           int(odo + 1u) >= step_limit || steps_done + 1 >= max_steps;
+        const uint64_t a2 = spec_move(L.row, L.code, b1, e, codes2);
+        const bool valid2 = !stop2 && (a2 != b1 || spec_overflow(codes2));
+        uint32_t idx2[F];
+        feature_indices<N>(a2, idx2);
+        float v2[F];
+        for_each_feature<N>([&](auto I) {
+            constexpr int i = decltype(I)::value;
+            v2[i] = valid2 ? __ldg(w + table_offset(N, i) + idx2[i]) : 0.0f;
+        });
+        // ---- in the shadow of the gathers: the spawn words of the two moves after these, the merge scores
+        const Philox4 p3 = spawn_words(g.seed, id, odo + 3u, 0u), p4 = spawn_words(g.seed, id, odo + 4u, 0u);
+        const uint32_t g1 = spec_gain(codes1), g2 = spec_gain(codes2);
+        const uint32_t f1 = ovf1 ? 2u : 0u, f2 = spec_overflow(codes2) ? 2u : 0u;
+        // ---- first move: argmax over d among the lanes (d, 0) (xor 4, xor 8), then everybody reads lane (0, 0)
+        float s1 = 0.0f;
+#pragma unroll
+        for (int i = 0; i < F; i++) s1 = __fadd_rn(s1, v1[i]);
+        float bv = need1 ? s1 : -INFINITY;
+        int bd = need1 ? d : 4;
+#pragma unroll
+        for (int off = 4; off < 16; off <<= 1) {
+            const float ov = __shfl_xor_sync(FULL, bv, off, 16);
+            const int od = __shfl_xor_sync(FULL, bd, off, 16);
+            if (od < 4 && (bd == 4 || ov > bv || (ov == bv && od < bd))) { bv = ov; bd = od; }
+        }
+        bd = __shfl_sync(FULL, bd, 0, 16);
+        const uint32_t nv1 = __popc((__ballot_sync(FULL, need1) >> gbase) & 0xFFFFu);
+        const int src1 = (bd & 3) << 2;                                // lane (bd, 0) of the half-warp
+        const uint64_t w_b1 = shfl64(b1, src1, 16);
+        const uint32_t w_g1 = __shfl_sync(FULL, g1, src1, 16), w_f1 = __shfl_sync(FULL, f1, src1, 16);
+        const bool w_stop2 = __shfl_sync(FULL, int(stop2), src1, 16) != 0;
+        float s2 = 0.0f;
+#pragma unroll
+        for (int i = 0; i < F; i++) s2 = __fadd_rn(s2, v2[i]);
+        // ---- second move: argmax over e inside the winning group (every lane reads the lane (bd, its own e))
+        float cv = __shfl_sync(FULL, valid2 ? s2 : -INFINITY, src1 + e, 16);
+        int ce = __shfl_sync(FULL, valid2 ? e : 4, src1 + e, 16);
+#pragma unroll
+        for (int off = 1; off < 4; off <<= 1) {
+            const float ov = __shfl_xor_sync(FULL, cv, off, 16);
+            const int oe = __shfl_xor_sync(FULL, ce, off, 16);
+            if (oe < 4 && (ce == 4 || ov > cv || (ov == cv && oe < ce))) { cv = ov; ce = oe; }
+        }
+        const uint32_t nv2 = __popc((__ballot_sync(FULL, valid2) >> (gbase + src1)) & 0xFu);
+        const int src2 = src1 + (ce & 3);
+        uint64_t w_a2 = shfl64(a2, src2, 16);
+        const uint32_t w_g2 = __shfl_sync(FULL, g2, src2, 16), w_f2 = __shfl_sync(FULL, f2, src2, 16);
+        int advanced = 0;
+        if (run && bd == 4) {                                       // no legal move (game over), limit tile or step limit
+            flags |= B2048_F_DONE;
+            run = false;
+            if (hl == 0) {
+                c_fin++; c_score += score; c_msum += odo;
+                atomicAdd(g.tile_hist + max_tile(board), 1u);
+                log_finished(g, id, score, odo, max_tile(board), board);
+            }
+        }
+        if (run) {
+            if (w_f1 & 2u) {                                        // the first move would create 2^16: flag + stop
+                flags |= B2048_F_DONE | B2048_F_OVERFLOW;
+                run = false;
+                if (hl == 0) {
+                    c_fin++; c_score += score; c_msum += odo; c_ovf++;
+                    atomicAdd(g.tile_hist + 16, 1u);
+                    log_finished(g, id, score, odo, 16u, board);
+                }
+            } else {
+                if (hl == 0) { c_moves++; c_evals += nv1; }
+                board = w_b1;
+                score += w_g1;
+                odo++;
+                steps_done++;
+                advanced = 1;
+                if (!w_stop2 && ce != 4) {                          // (ce == 4: the board after the first move is over)
+                    if (w_f2 & 2u) {
+                        flags |= B2048_F_DONE | B2048_F_OVERFLOW;
+                        run = false;
+                        if (hl == 0) {
+                            c_fin++; c_score += score; c_msum += odo; c_ovf++;
+                            atomicAdd(g.tile_hist + 16, 1u);
+                            log_finished(g, id, score, odo, 16u, board);
+                        }
+                    } else {
+                        if (hl == 0) { c_moves++; c_evals += nv2; }
+                        spawn_apply_nonempty(w_a2, p2.x, p2.y);
+                        board = w_a2;
+                        score += w_g2;
+                        odo++;
+                        steps_done++;
+                        advanced = 2;
+                    }
+                }
+            }
+        }
+        if (advanced == 2) { p1 = p3; p2 = p4; }
+        else if (advanced == 1) { p1 = p2; p2 = p3; }
+    }
+    if (in && hl == 0) {
         g.board[slot] = board;
         g.score[slot] = score;
         g.moves[slot] = odo;
@@ -1234,7 +1504,9 @@ __device__ __forceinline__ bool phase_a_compute(const float *__restrict__ w, con
             } else {
                 odo++;
                 Philox4 r = spawn_words(g.seed, id, odo, 0u);
-                sp = spawn_apply(board, r.x, r.y);
+                sp = 0;
+                if (trace_spawn) sp = spawn_apply(board, r.x, r.y);
+                else spawn_apply_nonempty(board, r.x, r.y);
             }
             if (d == 0 && trace_spawn && int64_t(odo) <= trace_len) trace_spawn[slot * trace_len + odo - 1] = uint16_t(sp);
         }
@@ -2161,6 +2433,16 @@ int greedy_play_impl(const float *w, const uint32_t *lut, const b2048_games_t *g
                      uint16_t *trace_spawn, int64_t trace_len, cudaStream_t st)
 {
     b2048_replay_t rp = replay ? *replay : b2048_replay_t{nullptr, nullptr, 0};
+    // small batches without replay / traces: the latency-oriented kernel (two moves per L2 round trip, 16 lanes per game)
+    if (!replay && !trace_dir && !trace_value && !trace_spawn && g->B <= int64_t(2) * sm_count() * (SPEC_THREADS / 16) &&
+        max_steps >= 2) {
+        cudaError_t e = cudaFuncSetAttribute(greedy_spec_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, LUT_SMEM_BYTES);
+        if (e != cudaSuccess) return int(e);
+        const int64_t want = cdiv(g->B * 16, SPEC_THREADS);
+        const unsigned grid = unsigned(want < sm_count() ? want : sm_count());
+        greedy_spec_kernel<N><<<grid, SPEC_THREADS, LUT_SMEM_BYTES, st>>>(w, lut, *g, max_steps, limit_tile, step_limit);
+        return launch_status();
+    }
     int occ = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, greedy_play_kernel<N>, 128, 0);
     if (e != cudaSuccess) return int(e);

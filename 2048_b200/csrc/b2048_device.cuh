@@ -315,6 +315,29 @@ __host__ __device__ __forceinline__ uint32_t spawn_apply(uint64_t &b, uint32_t r
     return (tile << 8) | uint32_t(15 - sh / 4);
 }
 
+// The same spawn for a board that holds at least one tile (every afterstate of a legal move does), without the binary
+// search and without a variable 64-bit shift: z * 0x1111...1 puts in nibble j the number of empty cells among nibbles
+// 0..j (at most 15, so no nibble overflows); the k-th empty cell in row-major order is the (m - k)-th from the least
+// significant end, i.e. the one empty nibble whose prefix count equals m - k.  Returns nothing (callers that record
+// the spawn use spawn_apply).
+__host__ __device__ __forceinline__ void spawn_apply_nonempty(uint64_t &b, uint32_t r_tile, uint32_t r_pos)
+{
+    const uint64_t z = zero_nibbles(b);
+    const int m = popc64(z);
+    if (m == 0) return;
+    const uint32_t k = umulhi32(r_pos, uint32_t(m));
+    const uint64_t prefix = z * 0x1111111111111111ULL;
+    const uint64_t want = uint64_t(uint32_t(m) - k) * 0x1111111111111111ULL;
+    const uint64_t hit = zero_nibbles(prefix ^ want) & z;             // one bit: bit 4j of the chosen nibble j
+    b |= umulhi32(r_tile, 10u) == 0 ? hit << 1 : hit;
+}
+
+// BASELINE config 5 (b2048_sweep) draws ONE Philox block per board, counter (index_lo, index_hi, 0, purpose 1), and
+// gives direction d the word d: its low half decides the tile, its high half the cell (16-bit fractions in the top
+// bits of the two arguments of spawn_apply: P("4") = 6554 / 65536).
+__host__ __device__ __forceinline__ uint32_t sweep_tile_word(uint32_t w) { return w << 16; }
+__host__ __device__ __forceinline__ uint32_t sweep_pos_word(uint32_t w) { return w & 0xFFFF0000u; }
+
 // Game.__init__ (game_logic.py:61-66): two spawns on the empty board
 __host__ __device__ __forceinline__ uint64_t spawn_initial(uint64_t seed, uint64_t id)
 {

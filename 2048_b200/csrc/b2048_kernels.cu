@@ -143,6 +143,22 @@ __global__ void spawn_replay_kernel(uint64_t *__restrict__ boards, int64_t m, co
 // config-5 sweep: persistent CTAs, row LUT (u16) + merge-code LUT (u8) staged in 192 KB of shared memory
 constexpr int SWEEP_THREADS = 1024;
 constexpr size_t SWEEP_SMEM = 65536 * 2 + 65536;
+#ifndef B2048_SWEEP_SWZ
+#define B2048_SWEEP_SWZ 1
+#endif
+// shared-memory slot of a line.  Lines of real boards are far from uniform (small tiles and empty cells dominate the low
+// nibbles, which select the bank), so with the identity mapping a warp's 32 lookups pile up on a few banks (6 wavefronts
+// per request on iid boards, more on boards from games).  XOR-ing the bank bits with the upper byte of the line spreads
+// them; the map is a bijection (each bit is XOR-ed only with higher bits).  The kernel applies it to the four lines of a
+// board at once (sweep_slots: 4 instructions per direction).
+__device__ __forceinline__ uint32_t sweep_slot(uint32_t line)
+{
+    return B2048_SWEEP_SWZ ? line ^ ((line >> 7) & 0x1FEu) : line;
+}
+__device__ __forceinline__ uint64_t sweep_slots(uint64_t x)
+{
+    return B2048_SWEEP_SWZ ? x ^ ((x >> 7) & 0x01FE01FE01FE01FEULL) : x;
+}
 
 __global__ void __launch_bounds__(SWEEP_THREADS, 1)
 sweep_kernel(const uint32_t *__restrict__ lut, const uint64_t *__restrict__ boards, int64_t m, uint64_t seed,
@@ -155,11 +171,21 @@ sweep_kernel(const uint32_t *__restrict__ lut, const uint64_t *__restrict__ boar
     // stage: 4 entries per thread per iteration (16 B global load -> 8 B + 4 B shared stores)
     for (int q = threadIdx.x; q < 65536 / 4; q += SWEEP_THREADS) {
         uint4 e = __ldg(reinterpret_cast<const uint4 *>(lut) + q);
-        uint2 r = make_uint2((e.x & 0xFFFFu) | (e.y << 16), (e.z & 0xFFFFu) | (e.w << 16));
-        reinterpret_cast<uint2 *>(srow)[q] = r;
-        uint32_t c = ((e.x >> 16) & 0xFFu) | (((e.y >> 16) & 0xFFu) << 8) | (((e.z >> 16) & 0xFFu) << 16) |
-                     (((e.w >> 16) & 0xFFu) << 24);
-        reinterpret_cast<uint32_t *>(scode)[q] = c;
+        if (B2048_SWEEP_SWZ) {
+            const uint32_t ev[4] = {e.x, e.y, e.z, e.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t slot = sweep_slot(4u * q + j);
+                srow[slot] = uint16_t(ev[j]);
+                scode[slot] = uint8_t(ev[j] >> 16);
+            }
+        } else {
+            uint2 r = make_uint2((e.x & 0xFFFFu) | (e.y << 16), (e.z & 0xFFFFu) | (e.w << 16));
+            reinterpret_cast<uint2 *>(srow)[q] = r;
+            uint32_t c = ((e.x >> 16) & 0xFFu) | (((e.y >> 16) & 0xFFu) << 8) | (((e.z >> 16) & 0xFFu) << 16) |
+                         (((e.w >> 16) & 0xFFu) << 24);
+            reinterpret_cast<uint32_t *>(scode)[q] = c;
+        }
     }
     __syncthreads();
     const int64_t stride = int64_t(gridDim.x) * SWEEP_THREADS;
@@ -176,9 +202,10 @@ sweep_kernel(const uint32_t *__restrict__ lut, const uint64_t *__restrict__ boar
         for (int d = 0; d < 4; d++) {
             uint64_t out = 0;
             uint32_t codes = 0;                                  // 8 merge exponents (2 per row), 0 = none
+            const uint64_t xs = sweep_slots(x[d]);
 #pragma unroll
             for (int r = 0; r < 4; r++) {
-                const uint32_t line = uint32_t(x[d] >> (48 - 16 * r)) & 0xFFFFu;
+                const uint32_t line = uint32_t(xs >> (48 - 16 * r)) & 0xFFFFu;
                 out |= uint64_t(srow[line]) << (48 - 16 * r);
                 if (d < 2) codes |= uint32_t(scode[line]) << (8 * r);
             }
@@ -211,15 +238,12 @@ sweep_kernel(const uint32_t *__restrict__ lut, const uint64_t *__restrict__ boar
         flags[i] = uint8_t(fl);
         if (spawned) {
             uint64_t idx = first_index + uint64_t(i);
-            if (ok & 3u) {
+            if (ok) {                                            // one Philox call per board, one word per direction
                 Philox4 w = spawn_words(seed, idx, 0u, 1u);
-                if (ok & 1u) spawn_apply(a[0], w.x, w.y);
-                if (ok & 2u) spawn_apply(a[1], w.z, w.w);
-            }
-            if (ok & 12u) {
-                Philox4 w = spawn_words(seed, idx, 1u, 1u);
-                if (ok & 4u) spawn_apply(a[2], w.x, w.y);
-                if (ok & 8u) spawn_apply(a[3], w.z, w.w);
+                const uint32_t wd[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                for (int d = 0; d < 4; d++)
+                    if ((ok >> d) & 1u) spawn_apply_nonempty(a[d], sweep_tile_word(wd[d]), sweep_pos_word(wd[d]));
             }
             ulonglong2 *sp = reinterpret_cast<ulonglong2 *>(spawned + 4 * i);
             sp[0] = make_ulonglong2(a[0], a[1]);

@@ -633,8 +633,9 @@ def greedy_bench(D, ctx, args, n, first_id, B, wd, steps, warmup, label, sampler
         torch.cuda.synchronize()
         if i:
             e_ms += a.elapsed_time(b); e_moves += c["moves"]
+    longest = float(games.moves.max().item()) if B else 0.0          # the longest game bounds a latency-bound step
     mx, sm = D.max_sum([ms, float(tot["moves"]), float(tot["evals"]), e_ms, float(e_moves), float(tot["score"]),
-                        float(tot["fin"])])
+                        float(tot["fin"]), longest])
     if D.rank != 0:
         return None
     ms, e_ms = mx[0], mx[3]
@@ -650,7 +651,8 @@ def greedy_bench(D, ctx, args, n, first_id, B, wd, steps, warmup, label, sampler
     res = {"metric": "expectimax_moves_per_sec" if look else "greedy_moves_per_sec", "value": value, "unit": "moves/s",
            "ms_per_step": ms / steps, "steps": steps, "warmup": warmup,
            "config": {"workload": label, "n": n, "games_this_rank": B, "moves_per_game": moves / max(sm[6], 1),
-                      "avg_score": sm[5] / max(sm[6], 1),
+                      "avg_score": sm[5] / max(sm[6], 1), "longest_game_moves": mx[7],
+                      "us_per_move_of_longest_game": ms / steps * 1e3 / max(mx[7], 1),
                       "l2": "a 256 MiB buffer is written between timed steps to flush L2"},
            "clocks": clocks,
            "e2e": {"value": e_moves / (e_ms * 1e-3) if e_ms else None, "unit": "moves/s", "h2d_bytes_per_step": nw_bytes,

@@ -93,8 +93,8 @@ int b2048_spawn_replay(uint64_t *boards, int64_t m, const uint8_t *tile, const u
                        b2048_stream_t stream);
 
 /* BASELINE config 5: move4 + a Philox spawn on every changed, non-overflowing afterstate, one pass.
- * spawn stream: counter = (index_lo, index_hi, d>>1, purpose 1), words 2(d&1), 2(d&1)+1, with
- * index = first_index + i.  spawned [m,4] (NULL = no spawn pass).  Row LUTs are staged in shared
+ * spawn stream: ONE Philox block per board, counter = (index_lo, index_hi, 0, purpose 1), index = first_index + i;
+ * direction d takes word d (low 16 bits: tile fraction, high 16 bits: cell fraction).  spawned [m,4] (NULL = no spawn pass).  Row LUTs are staged in shared
  * memory by a persistent grid. */
 int b2048_sweep(const uint32_t *lut, const uint64_t *boards, int64_t m, uint64_t seed, uint64_t first_index,
                 uint64_t *after, uint32_t *gain, uint8_t *flags, uint64_t *spawned, b2048_stream_t stream);

@@ -374,13 +374,13 @@ int orc_spawn_move(uint64_t seed, uint64_t id, uint32_t move_no, int32_t *row)
     return orc_spawn_apply(row, w[0], w[1]);
 }
 
-/* sweep spawn (BASELINE config 5): board index i, direction d -> purpose 1, counter z = d>>1,
- * words 2*(d&1), 2*(d&1)+1 */
+/* sweep spawn (BASELINE config 5): ONE Philox block per board index i (purpose 1, counter z = 0); direction d takes
+ * word d, low 16 bits -> tile fraction, high 16 bits -> cell fraction (both as the top half of a 32-bit word) */
 int orc_spawn_sweep(uint64_t seed, uint64_t index, int d, int32_t *row)
 {
     uint32_t w[4];
-    orc_spawn_words(seed, index, (uint32_t)(d >> 1), 1, w);
-    return orc_spawn_apply(row, w[2 * (d & 1)], w[2 * (d & 1) + 1]);
+    orc_spawn_words(seed, index, 0, 1, w);
+    return orc_spawn_apply(row, w[d & 3] << 16, w[d & 3] & 0xFFFF0000u);
 }
 
 /*

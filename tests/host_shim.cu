@@ -137,7 +137,17 @@ uint32_t hs_spawn_move(uint64_t seed, uint64_t id, uint32_t move_no, uint64_t *b
 
 uint32_t hs_spawn_sweep(uint64_t seed, uint64_t index, int d, uint64_t *b)
 {
-    Philox4 r = spawn_words(seed, index, uint32_t(d >> 1), 1u);
-    return (d & 1) ? spawn_apply(*b, r.z, r.w) : spawn_apply(*b, r.x, r.y);
+    Philox4 r = spawn_words(seed, index, 0u, 1u);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+    return spawn_apply(*b, sweep_tile_word(w[d & 3]), sweep_pos_word(w[d & 3]));
+}
+
+// the two spawn routines must agree on every board that holds a tile
+int hs_spawn_nonempty_agrees(uint64_t b, uint32_t r_tile, uint32_t r_pos)
+{
+    uint64_t b1 = b, b2 = b;
+    spawn_apply(b1, r_tile, r_pos);
+    spawn_apply_nonempty(b2, r_tile, r_pos);
+    return b1 == b2;
 }
 }

@@ -29,6 +29,7 @@ def hs():
     lib.hs_spawn_move.restype = C.c_uint32
     lib.hs_spawn_sweep.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
     lib.hs_spawn_sweep.restype = C.c_uint32
+    lib.hs_spawn_nonempty_agrees.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32]
     lib.hs_d4.argtypes = [C.c_uint64, C.c_void_p]
     lib.hs_move4.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64] + [C.c_void_p] * 4
     lib.hs_stats.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
@@ -177,3 +178,17 @@ def test_philox_and_spawns_match_oracle(hs, orc, fx):
         r2 = row.reshape(16).copy()
         orc.lib().orc_spawn_sweep(7, 1000 + i, i % 4, r2.ctypes.data_as(C.POINTER(C.c_int32)))
         assert b[0] == orc.pack_np(r2.reshape(1, 4, 4))[0]
+    # the search-free spawn used in the hot loops (boards with at least one tile) == the general one: 1..15 empty cells
+    # in every position pattern class, every k, both tiles
+    rs = np.random.RandomState(11)
+    for _ in range(20000):
+        cells = rs.randint(0, 16, 16) * (rs.random_sample(16) < rs.random_sample())
+        if not cells.any():
+            cells[rs.randint(16)] = 1 + rs.randint(15)
+        b = int(orc.pack_np(cells.reshape(1, 4, 4).astype(np.int32))[0])
+        assert hs.hs_spawn_nonempty_agrees(b, int(rs.randint(0, 2 ** 32, dtype=np.uint64)), int(rs.randint(0, 2 ** 32, dtype=np.uint64)))
+    for pos in range(16):                                         # exactly one tile: 15 empties, every k
+        b = 3 << (4 * pos)
+        for k in range(15):
+            r_pos = ((k << 32) // 15 + 1) & 0xFFFFFFFF
+            assert hs.hs_spawn_nonempty_agrees(b, 0, r_pos) and hs.hs_spawn_nonempty_agrees(b, 2 ** 31, r_pos)
