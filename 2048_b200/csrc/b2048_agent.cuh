@@ -414,6 +414,35 @@ __device__ __forceinline__ void log_finished(const b2048_games_t &g, uint64_t id
     }
 }
 
+struct LutShared {
+    const uint16_t *row;
+    const uint8_t *code;
+    // the entry in b2048_lut_build's format, rebuilt from the two shared-memory tables
+    __device__ __forceinline__ uint32_t operator()(uint32_t line) const
+    {
+        const uint32_t r = row[line], c = code[line];
+        uint32_t t = c & (c >> 1);
+        t &= t >> 2;                                       // bit 0 / 4: that merge exponent is 15 (a 2^16 would appear)
+        const uint32_t ovf = (t & 0x11u) ? 1u : 0u;
+        return r | (c << 16) | (uint32_t((r != line) | ovf) << 24) | (ovf << 25);
+    }
+};
+
+constexpr int LUT_SMEM_BYTES = 65536 * 2 + 65536;
+
+__device__ __forceinline__ void stage_lut_shared(const uint32_t *__restrict__ lut, unsigned char *smem)
+{
+    uint16_t *srow = reinterpret_cast<uint16_t *>(smem);
+    uint8_t *scode = smem + 65536 * 2;
+    for (int q = threadIdx.x; q < 65536 / 4; q += blockDim.x) {
+        const uint4 e = __ldg(reinterpret_cast<const uint4 *>(lut) + q);
+        reinterpret_cast<uint2 *>(srow)[q] = make_uint2((e.x & 0xFFFFu) | (e.y << 16), (e.z & 0xFFFFu) | (e.w << 16));
+        reinterpret_cast<uint32_t *>(scode)[q] = ((e.x >> 16) & 0xFFu) | (((e.y >> 16) & 0xFFu) << 8) |
+                                                 (((e.z >> 16) & 0xFFu) << 16) | (((e.w >> 16) & 0xFFu) << 24);
+    }
+    __syncthreads();
+}
+
 // One afterstate per lane (lane d of a 4-lane group = direction d), value by n-tuple gather, then a
 // width-4 shuffle argmax with the reference's tie rule (strict '>' scanning d = 0..3: lowest d wins).
 // Split in two so that the persistent trainer can do the weight-independent half (LUT move, table indices)
@@ -425,8 +454,8 @@ struct MovePrep {
     uint32_t idx[num_feat(N)];
 };
 
-template <int N>
-__device__ __forceinline__ void move_prepare(const LutGlobal &L, uint64_t board, int d, MovePrep<N> &p)
+template <int N, class LutT>
+__device__ __forceinline__ void move_prepare(const LutT &L, uint64_t board, int d, MovePrep<N> &p)
 {
     p.gain = 0;
     p.fl = 0;
@@ -459,8 +488,8 @@ __device__ __forceinline__ void best_move_finish(const float *__restrict__ w, co
     best_dir = bd;
 }
 
-template <int N, bool COHERENT = false>
-__device__ __forceinline__ void best_move(const float *__restrict__ w, const LutGlobal &L, uint64_t board, int d,
+template <int N, bool COHERENT = false, class LutT = LutGlobal>
+__device__ __forceinline__ void best_move(const float *__restrict__ w, const LutT &L, uint64_t board, int d,
                                           bool run, uint64_t &best_after, uint32_t &best_gain, float &best_value,
                                           int &best_dir, uint32_t &best_flags, uint32_t &n_valid)
 {
@@ -476,16 +505,24 @@ __device__ __forceinline__ void best_move(const float *__restrict__ w, const Lut
 // persistent and the 4-lane groups take game slots from a queue (g.counters[B2048_CTR_QUEUE]): games end after
 // very different numbers of moves, and with a fixed slot per group a warp would idle until the longest of its 8
 // games is over.  A slot is played until it is DONE or has made max_steps moves in this launch, then written back.
-template <int N>
-__global__ void __launch_bounds__(128, B2048_GREEDY_MINBLOCKS)
+// SMEM_LUT: one CTA of GREEDY_WIDE_THREADS per SM with the row LUT staged in 192 KB of shared memory, instead of several
+// 128-thread CTAs reading it through L1 (lab variant: profiles/r02_greedy_lut_placement.txt has the comparison)
+constexpr int GREEDY_WIDE_THREADS = 768;
+template <int N, bool SMEM_LUT>
+__global__ void __launch_bounds__(SMEM_LUT ? GREEDY_WIDE_THREADS : 128, SMEM_LUT ? 1 : B2048_GREEDY_MINBLOCKS)
 greedy_play_kernel(const float *__restrict__ w, const uint32_t *__restrict__ lut, b2048_games_t g, int max_steps,
                    int limit_tile, int step_limit, b2048_replay_t rp, int has_replay, int8_t *__restrict__ trace_dir,
                    float *__restrict__ trace_value, uint16_t *__restrict__ trace_spawn, int64_t trace_len)
 {
+    extern __shared__ __align__(16) unsigned char greedy_smem[];
+    if (SMEM_LUT) stage_lut_shared(lut, greedy_smem);
     const int lane = threadIdx.x & 31, d = lane & 3;
     const unsigned gmask = 0xFu << (lane & ~3);
     unsigned long long *queue = reinterpret_cast<unsigned long long *>(g.counters + B2048_CTR_QUEUE);
-    LutGlobal L{lut};
+    using LutT = std::conditional_t<SMEM_LUT, LutShared, LutGlobal>;
+    LutT L;
+    if constexpr (SMEM_LUT) L = LutShared{reinterpret_cast<const uint16_t *>(greedy_smem), greedy_smem + 65536 * 2};
+    else L = LutGlobal{lut};
     int64_t slot = -1;
     uint64_t board = 0, id = 0;
     uint32_t score = 0, odo = 0, flags = B2048_F_DONE;
@@ -539,7 +576,7 @@ greedy_play_kernel(const float *__restrict__ w, const uint32_t *__restrict__ lut
         uint32_t bg, bf, nv;
         float bv;
         int bd;
-        best_move<N>(w, L, board, d, run, ba, bg, bv, bd, bf, nv);
+        best_move<N, false, LutT>(w, L, board, d, run, ba, bg, bv, bd, bf, nv);
         if (run) {
             if (bf & 2u) {                                          // 2^16 escape: flag + stop
                 flags |= B2048_F_DONE | B2048_F_OVERFLOW;
@@ -609,35 +646,6 @@ greedy_play_kernel(const float *__restrict__ w, const uint32_t *__restrict__ lut
 // bit-identical; 5x the gather traffic is what the otherwise idle L2 pays for halving the latency per move.
 // No replay / trace support: the launcher takes greedy_play_kernel for those.
 // ------------------------------------------------------------------------------------------------
-struct LutShared {
-    const uint16_t *row;
-    const uint8_t *code;
-    // the entry in b2048_lut_build's format, rebuilt from the two shared-memory tables
-    __device__ __forceinline__ uint32_t operator()(uint32_t line) const
-    {
-        const uint32_t r = row[line], c = code[line];
-        uint32_t t = c & (c >> 1);
-        t &= t >> 2;                                       // bit 0 / 4: that merge exponent is 15 (a 2^16 would appear)
-        const uint32_t ovf = (t & 0x11u) ? 1u : 0u;
-        return r | (c << 16) | (uint32_t((r != line) | ovf) << 24) | (ovf << 25);
-    }
-};
-
-constexpr int LUT_SMEM_BYTES = 65536 * 2 + 65536;
-
-__device__ __forceinline__ void stage_lut_shared(const uint32_t *__restrict__ lut, unsigned char *smem)
-{
-    uint16_t *srow = reinterpret_cast<uint16_t *>(smem);
-    uint8_t *scode = smem + 65536 * 2;
-    for (int q = threadIdx.x; q < 65536 / 4; q += blockDim.x) {
-        const uint4 e = __ldg(reinterpret_cast<const uint4 *>(lut) + q);
-        reinterpret_cast<uint2 *>(srow)[q] = make_uint2((e.x & 0xFFFFu) | (e.y << 16), (e.z & 0xFFFFu) | (e.w << 16));
-        reinterpret_cast<uint32_t *>(scode)[q] = ((e.x >> 16) & 0xFFu) | (((e.y >> 16) & 0xFFu) << 8) |
-                                                 (((e.z >> 16) & 0xFFu) << 16) | (((e.w >> 16) & 0xFFu) << 24);
-    }
-    __syncthreads();
-}
-
 // slide+merge in direction d from the two shared-memory tables: the afterstate, whether it differs from the board, and
 // the four merge-code bytes of its lines (spec_gain / spec_overflow decode them later, off the critical path)
 __device__ __forceinline__ uint64_t spec_move(const uint16_t *__restrict__ srow, const uint8_t *__restrict__ scode,
@@ -2443,13 +2451,24 @@ int greedy_play_impl(const float *w, const uint32_t *lut, const b2048_games_t *g
         greedy_spec_kernel<N><<<grid, SPEC_THREADS, LUT_SMEM_BYTES, st>>>(w, lut, *g, max_steps, limit_tile, step_limit);
         return launch_status();
     }
+#ifdef B2048_GREEDY_SMEM_LUT                                          // lab build: row LUT in shared memory, 1 wide CTA per SM
+    {
+        cudaError_t e = cudaFuncSetAttribute(greedy_play_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LUT_SMEM_BYTES);
+        if (e != cudaSuccess) return int(e);
+        const int64_t want = cdiv(g->B * 4, GREEDY_WIDE_THREADS);
+        const unsigned grid = unsigned(want < sm_count() ? want : sm_count());
+        greedy_play_kernel<N, true><<<grid, GREEDY_WIDE_THREADS, LUT_SMEM_BYTES, st>>>(w, lut, *g, max_steps, limit_tile, step_limit, rp,
+                                                                                   replay ? 1 : 0, trace_dir, trace_value, trace_spawn, trace_len);
+        return launch_status();
+    }
+#endif
     int occ = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, greedy_play_kernel<N>, 128, 0);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, greedy_play_kernel<N, false>, 128, 0);
     if (e != cudaSuccess) return int(e);
     const int64_t want = cdiv(g->B * 4, 128), cap = int64_t(sm_count()) * (occ > 0 ? occ : 1);
     const unsigned grid = unsigned(want < cap ? want : cap);           // persistent: groups pull slots from the queue
-    greedy_play_kernel<N><<<grid, 128, 0, st>>>(w, lut, *g, max_steps, limit_tile, step_limit, rp, replay ? 1 : 0, trace_dir,
-                                               trace_value, trace_spawn, trace_len);
+    greedy_play_kernel<N, false><<<grid, 128, 0, st>>>(w, lut, *g, max_steps, limit_tile, step_limit, rp, replay ? 1 : 0, trace_dir,
+                                                      trace_value, trace_spawn, trace_len);
     return launch_status();
 }
 

@@ -329,7 +329,7 @@ __host__ __device__ __forceinline__ void spawn_apply_nonempty(uint64_t &b, uint3
     const uint64_t prefix = z * 0x1111111111111111ULL;
     const uint64_t want = uint64_t(uint32_t(m) - k) * 0x1111111111111111ULL;
     const uint64_t hit = zero_nibbles(prefix ^ want) & z;             // one bit: bit 4j of the chosen nibble j
-    b |= umulhi32(r_tile, 10u) == 0 ? hit << 1 : hit;
+    b |= hit * uint64_t(umulhi32(r_tile, 10u) == 0 ? 2u : 1u);       // (a multiply: the shifter pipe is the busy one)
 }
 
 // BASELINE config 5 (b2048_sweep) draws ONE Philox block per board, counter (index_lo, index_hi, 0, purpose 1), and

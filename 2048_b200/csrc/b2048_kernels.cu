@@ -142,7 +142,7 @@ __global__ void spawn_replay_kernel(uint64_t *__restrict__ boards, int64_t m, co
 
 // config-5 sweep: persistent CTAs, row LUT (u16) + merge-code LUT (u8) staged in 192 KB of shared memory
 constexpr int SWEEP_THREADS = 1024;
-constexpr size_t SWEEP_SMEM = 65536 * 2 + 65536;
+constexpr size_t SWEEP_SMEM = 65536 * 2 + 65536 + 256 * 4;   // lines u16, merge codes u8, score of a code u32
 #ifndef B2048_SWEEP_SWZ
 #define B2048_SWEEP_SWZ 1
 #endif
@@ -168,6 +168,14 @@ sweep_kernel(const uint32_t *__restrict__ lut, const uint64_t *__restrict__ boar
     extern __shared__ __align__(16) unsigned char smem[];
     uint16_t *srow = reinterpret_cast<uint16_t *>(smem);
     uint8_t *scode = smem + 65536 * 2;
+    // score of a merge-code byte (two exponents): bits 0-23 the merge score 2^(a+1) + 2^(b+1), bits 24+ the number of
+    // exponents equal to 15 (a 2^16 would appear); the four lines of a direction just add their entries.  The sweep is
+    // bound by the integer-logic pipe (ncu: ALU pipe 81 % busy), so a second small lookup beats decoding 8 nibbles.
+    uint32_t *sscore = reinterpret_cast<uint32_t *>(smem + 65536 * 3);
+    if (threadIdx.x < 256) {
+        const uint32_t a = threadIdx.x & 15u, b = threadIdx.x >> 4;
+        sscore[threadIdx.x] = (((2u << a) & ~2u) + ((2u << b) & ~2u)) | ((uint32_t(a == 15u) + uint32_t(b == 15u)) << 24);
+    }
     // stage: 4 entries per thread per iteration (16 B global load -> 8 B + 4 B shared stores)
     for (int q = threadIdx.x; q < 65536 / 4; q += SWEEP_THREADS) {
         uint4 e = __ldg(reinterpret_cast<const uint4 *>(lut) + q);
@@ -201,25 +209,20 @@ sweep_kernel(const uint32_t *__restrict__ lut, const uint64_t *__restrict__ boar
 #pragma unroll
         for (int d = 0; d < 4; d++) {
             uint64_t out = 0;
-            uint32_t codes = 0;                                  // 8 merge exponents (2 per row), 0 = none
+            uint32_t tot = 0;                                    // sum of the four lines' score entries
             const uint64_t xs = sweep_slots(x[d]);
 #pragma unroll
             for (int r = 0; r < 4; r++) {
                 const uint32_t line = uint32_t(xs >> (48 - 16 * r)) & 0xFFFFu;
                 out |= uint64_t(srow[line]) << (48 - 16 * r);
-                if (d < 2) codes |= uint32_t(scode[line]) << (8 * r);
+                if (d < 2) tot += sscore[scode[line]];
             }
             // Merges pair up equal neighbours inside maximal runs of equal tiles, floor(L / 2) per run from either
             // end, so the merge score and the 2^16 escape of right / down equal those of left / up: only the
             // afterstate and the changed flag depend on the side.  (Checked exhaustively against the oracle.)
             if (d < 2) {
-                uint32_t t = codes & (codes >> 1);
-                t &= t >> 2;
-                ovf2[d] = (t & 0x11111111u) != 0;                // a 15+15 merge
-                uint32_t sc = 0;                                 // score += 2^(e+1) per merge (game_logic.py:33)
-#pragma unroll
-                for (int q = 0; q < 8; q++) sc += (2u << ((codes >> (4 * q)) & 15u)) & ~2u;
-                g[d] = sc;
+                ovf2[d] = (tot >> 24) != 0;                      // a 15+15 merge
+                g[d] = tot & 0xFFFFFFu;                          // score += 2^(e+1) per merge (game_logic.py:33)
             } else {
                 g[d] = g[d - 2];
             }
