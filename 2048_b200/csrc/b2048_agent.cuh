@@ -1685,12 +1685,23 @@ __device__ __forceinline__ bool peer_sync_in_kernel(const PeerSync &ps, uint32_t
 }
 
 // ---- dense small-exponent key space --------------------------------------------------------------
+// Keys whose cells are all below HL = hot_levels(n) ("small" keys) are accumulated per CTA in shared memory and merged
+// through a dense global table.  HL = 5 (cells 0..4, radix-5 index) where the table fits next to everything else
+// (n <= 4: 10,625 keys at n = 4), HL = 4 (cells 0..3, two bits per cell) otherwise.  Measured (r02): HL = 5 makes the
+// generic layout 5-6 % faster at n <= 4 but the one-round layout of the headline shape 13 % slower (more shared-memory
+// CAS atomics and flush REDs than L2 chains saved), so HL = 4 is the default everywhere; B2048_HOT_LEVELS_SMALL_N=5 selects
+// the n <= 4 choice (lab builds).
+#ifndef B2048_HOT_LEVELS_SMALL_N
+#define B2048_HOT_LEVELS_SMALL_N 4
+#endif
+__host__ __device__ constexpr int hot_levels(int n) { return n <= 4 ? B2048_HOT_LEVELS_SMALL_N : 4; }
+__host__ __device__ constexpr int ipow(int b, int e) { return e == 0 ? 1 : b * ipow(b, e - 1); }
 __host__ __device__ constexpr int small_tables(int n) { return n == 6 ? 21 : num_feat(n); }   // base-16 tables only
 __host__ __device__ constexpr int tuple_cells(int n, int i) { return n <= 3 ? n : i < 17 ? 4 : i < 21 ? 5 : 6; }
 __host__ __device__ constexpr int small_offset(int n, int i)            // first dense index of table i
 {
     int o = 0;
-    for (int k = 0; k < i && k < small_tables(n); k++) o += 1 << (2 * tuple_cells(n, k));
+    for (int k = 0; k < i && k < small_tables(n); k++) o += ipow(hot_levels(n), tuple_cells(n, k));
     return o;
 }
 __host__ __device__ constexpr int small_count(int n) { return small_offset(n, small_tables(n)); }
@@ -1706,14 +1717,50 @@ __device__ __forceinline__ uint32_t table_offset_rt(int i)
 template <int N>
 __device__ __forceinline__ int small_offset_rt(int i)
 {
-    if (N <= 4) return i << (2 * N);
+    if (N <= 4) return i * ipow(hot_levels(N), N);
     return i <= 17 ? i << 8 : (17 << 8) + ((i - 17) << 10);
+}
+
+// is every cell of the base-16 key v (ncell nibbles) small?
+template <int N>
+__device__ __forceinline__ bool small_key(uint32_t v, uint32_t big_mask)
+{
+    if (hot_levels(N) == 4) return (v & big_mask) == 0;
+    // HL = 5: no nibble >= 8, and no nibble in 5..7 (bit 2 set together with bit 1 or bit 0)
+    return ((v & 0x88888888u) | ((v >> 2) & ((v >> 1) | v) & 0x11111111u)) == 0;
+}
+
+// dense index of a small key inside its table
+template <int N, int MAXC>
+__device__ __forceinline__ uint32_t small_compact(uint32_t v)
+{
+    uint32_t cmp = 0;
+    if (hot_levels(N) == 4) {
+#pragma unroll
+        for (int k = 0; k < MAXC; k++) cmp |= ((v >> (4 * k)) & 3u) << (2 * k);
+    } else {
+#pragma unroll
+        for (int k = MAXC - 1; k >= 0; k--) cmp = cmp * 5u + ((v >> (4 * k)) & 15u);
+    }
+    return cmp;
 }
 
 // dense index -> weight index (inverse of the compaction in phase B)
 template <int N>
 __device__ __forceinline__ uint32_t small_to_key(int dense)
 {
+    if (hot_levels(N) != 4) {                          // n <= 4: every tuple has N cells, radix hot_levels(N)
+        constexpr int P = ipow(hot_levels(N), N);
+        const int tab = dense / P;
+        int compact = dense - tab * P;
+        uint32_t idx = 0;
+#pragma unroll
+        for (int k = 0; k < N; k++) {
+            idx |= uint32_t(compact % hot_levels(N)) << (4 * k);
+            compact /= hot_levels(N);
+        }
+        return table_offset_rt<N>(tab) + idx;
+    }
     int tab, compact, cells;
     if (N <= 4) { tab = dense >> (2 * N); compact = dense & ((1 << (2 * N)) - 1); cells = N; }
     else if (dense < (17 << 8)) { tab = dense >> 8; compact = dense & 255; cells = 4; }
@@ -1915,11 +1962,8 @@ td_persist_kernel(PersistBuffers pb, PersistCtrl *ctrl, const uint32_t *__restri
                 oldu[s] = 1u;
                 oldc[s] = 1u;
                 if (!live) continue;
-                if ((v & big_mask) == 0 && !base14) {         // small-exponent key: shared memory
-                    uint32_t cmp = 0;
-#pragma unroll
-                    for (int k = 0; k < MAXC; k++) cmp |= ((v >> (4 * k)) & 3u) << (2 * k);
-                    const int di = dense_off + int(cmp);
+                if (!base14 && small_key<N>(v, big_mask)) {   // small-exponent key: shared memory
+                    const int di = dense_off + int(small_compact<N, MAXC>(v));
                     if (EXACT) atomicAdd(s_q + di, (unsigned long long)qd); else atomicAdd(s_sum + di, d);
                     if (ld) oldc[s] = atomicAdd(s_cnt + di, 1u);
                 } else {
@@ -1971,12 +2015,7 @@ td_persist_kernel(PersistBuffers pb, PersistCtrl *ctrl, const uint32_t *__restri
 #pragma unroll
                     for (int s = 0; s < 8; s++) {
                         if ((first >> s) & 1u) list[pf++] = key_off + idx[s];
-                        if ((dirty >> s) & 1u) {
-                            uint32_t cmp = 0;
-#pragma unroll
-                            for (int k = 0; k < MAXC; k++) cmp |= ((idx[s] >> (4 * k)) & 3u) << (2 * k);
-                            s_dirty[pd++] = uint16_t(dense_off + int(cmp));
-                        }
+                        if ((dirty >> s) & 1u) s_dirty[pd++] = uint16_t(dense_off + int(small_compact<N, MAXC>(idx[s])));
                     }
                 }
             }
@@ -2006,12 +2045,7 @@ td_persist_kernel(PersistBuffers pb, PersistCtrl *ctrl, const uint32_t *__restri
             if (FAST) {
 #pragma unroll
                 for (int s = 0; s < 8; s++)
-                    if ((dirty >> s) & 1u) {
-                        uint32_t cmp = 0;
-#pragma unroll
-                        for (int k = 0; k < MAXC; k++) cmp |= ((idx[s] >> (4 * k)) & 3u) << (2 * k);
-                        flush_entry(dense_off + int(cmp));
-                    }
+                    if ((dirty >> s) & 1u) flush_entry(dense_off + int(small_compact<N, MAXC>(idx[s])));
             } else {
                 const uint32_t nd = s_ndirty;
                 for (uint32_t t = threadIdx.x; t < nd; t += blockDim.x) flush_entry(s_dirty[t]);

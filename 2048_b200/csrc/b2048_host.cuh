@@ -106,7 +106,7 @@ inline WorkLayout work_layout(int n, int64_t m, int mode)
     }
     // persistent trainer: per-CTA key lists, entries_per_CTA * 8F keys each (PERSIST_MAX_GRID CTAs at most)
     L.lists = o; o += align256(size_t(m + 4 * PERSIST_MAX_GRID) * 8 * num_feat(n) * 4);
-    L.hot = o; o += align256(size_t(17 * 256 + 4 * 1024) * 12);      // dense table of the small-exponent keys
+    L.hot = o; o += align256(size_t(10752) * 12);                    // dense table of the small-exponent keys (<= 10,625)
     L.total = o;
     return L;
 }
