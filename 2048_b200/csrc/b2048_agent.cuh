@@ -651,8 +651,11 @@ greedy_play_kernel(const float *__restrict__ w, const uint32_t *__restrict__ lut
 __device__ __forceinline__ uint64_t spec_move(const uint16_t *__restrict__ srow, const uint8_t *__restrict__ scode,
                                               uint64_t b, int d, uint32_t &codes)
 {
-    uint64_t x = (d & 1) ? transpose(b) : b;
-    if (d & 2) x = flip_h(x);
+    // branch-free: the lanes of a warp hold all four directions, so a branch around a transform would diverge anyway
+    // and, with one warp per scheduler, cost ~10 cycles of the chain each; masks select instead
+    const uint64_t mt = 0 - uint64_t(d & 1), mf = 0 - uint64_t((d >> 1) & 1);
+    uint64_t x = b ^ ((b ^ transpose(b)) & mt);
+    x ^= (x ^ flip_h(x)) & mf;
     uint64_t out = 0;
     codes = 0;
 #pragma unroll
@@ -661,8 +664,8 @@ __device__ __forceinline__ uint64_t spec_move(const uint16_t *__restrict__ srow,
         out |= uint64_t(srow[line]) << (48 - 16 * r);
         codes |= uint32_t(scode[line]) << (8 * r);
     }
-    if (d & 2) out = flip_h(out);
-    return (d & 1) ? transpose(out) : out;
+    out ^= (out ^ flip_h(out)) & mf;
+    return out ^ ((out ^ transpose(out)) & mt);
 }
 
 __device__ __forceinline__ bool spec_overflow(uint32_t codes)        // some merge exponent is 15: a 2^16 would appear
@@ -742,28 +745,31 @@ greedy_spec_kernel(const float *__restrict__ w, const uint32_t *__restrict__ lut
         const uint64_t a1 = spec_move(L.row, L.code, board, d, codes1);
         const bool valid1 = run && !limit_hit && (a1 != board || spec_overflow(codes1));
         const bool need1 = valid1 && e == 0;                           // lane (d, 0) scores a_d
+        // (the gathers are unconditional: a lane without a legal afterstate reads entry 0 of every table and its sum is
+        //  ignored -- a predicated load would put a divergent branch around each group of loads, and with one warp per
+        //  scheduler every branch costs ~10 cycles of the chain)
         uint32_t idx1[F];
-        feature_indices<N>(a1, idx1);
+        feature_indices<N>(need1 ? a1 : 0ULL, idx1);
         float v1[F];
         for_each_feature<N>([&](auto I) {
             constexpr int i = decltype(I)::value;
-            v1[i] = need1 ? __ldg(w + table_offset(N, i) + idx1[i]) : 0.0f;
+            v1[i] = __ldg(w + table_offset(N, i) + idx1[i]);
         });
         // ---- second level: the board after the spawn that WOULD follow a_d, and its move in direction e
         const bool ovf1 = spec_overflow(codes1);
         uint64_t b1 = a1;
-        if (valid1 && !ovf1) spawn_apply_nonempty(b1, p1.x, p1.y);
+        spawn_apply_nonempty(b1, p1.x, p1.y);                           // (only used where the first move is legal)
         // the second move exists only if the first one is legal, the game may go on after it and this launch may play it
         const bool stop2 = !valid1 || ovf1 || (limit_tile && max_tile(b1) >= limit_tile) ||
                            int(odo + 1u) >= step_limit || steps_done + 1 >= max_steps;
         const uint64_t a2 = spec_move(L.row, L.code, b1, e, codes2);
         const bool valid2 = !stop2 && (a2 != b1 || spec_overflow(codes2));
         uint32_t idx2[F];
-        feature_indices<N>(a2, idx2);
+        feature_indices<N>(valid2 ? a2 : 0ULL, idx2);
         float v2[F];
         for_each_feature<N>([&](auto I) {
             constexpr int i = decltype(I)::value;
-            v2[i] = valid2 ? __ldg(w + table_offset(N, i) + idx2[i]) : 0.0f;
+            v2[i] = __ldg(w + table_offset(N, i) + idx2[i]);
         });
         // ---- in the shadow of the gathers: the spawn words of the two moves after these, the merge scores
         const Philox4 p3 = spawn_words(g.seed, id, odo + 3u, 0u), p4 = spawn_words(g.seed, id, odo + 4u, 0u);
@@ -779,7 +785,9 @@ greedy_spec_kernel(const float *__restrict__ w, const uint32_t *__restrict__ lut
         for (int off = 4; off < 16; off <<= 1) {
             const float ov = __shfl_xor_sync(FULL, bv, off, 16);
             const int od = __shfl_xor_sync(FULL, bd, off, 16);
-            if (od < 4 && (bd == 4 || ov > bv || (ov == bv && od < bd))) { bv = ov; bd = od; }
+            const bool take = (od < 4) & ((bd == 4) | (ov > bv) | ((ov == bv) & (od < bd)));     // no short circuit
+            bv = take ? ov : bv;
+            bd = take ? od : bd;
         }
         bd = __shfl_sync(FULL, bd, 0, 16);
         const uint32_t nv1 = __popc((__ballot_sync(FULL, need1) >> gbase) & 0xFFFFu);
@@ -797,7 +805,9 @@ greedy_spec_kernel(const float *__restrict__ w, const uint32_t *__restrict__ lut
         for (int off = 1; off < 4; off <<= 1) {
             const float ov = __shfl_xor_sync(FULL, cv, off, 16);
             const int oe = __shfl_xor_sync(FULL, ce, off, 16);
-            if (oe < 4 && (ce == 4 || ov > cv || (ov == cv && oe < ce))) { cv = ov; ce = oe; }
+            const bool take = (oe < 4) & ((ce == 4) | (ov > cv) | ((ov == cv) & (oe < ce)));
+            cv = take ? ov : cv;
+            ce = take ? oe : ce;
         }
         const uint32_t nv2 = __popc((__ballot_sync(FULL, valid2) >> (gbase + src1)) & 0xFu);
         const int src2 = src1 + (ce & 3);

@@ -230,9 +230,14 @@ __host__ __device__ __forceinline__ uint64_t move_right(const LutT &lut, uint64_
 template <class LutT>
 __host__ __device__ __forceinline__ uint64_t move_dir(const LutT &lut, uint64_t b, int d, uint32_t &gain, uint32_t &flags)
 {
-    uint64_t x = (d & 1) ? transpose(b) : b;
-    uint64_t y = (d & 2) ? move_right(lut, x, gain, flags) : move_left(lut, x, gain, flags);
-    return (d & 1) ? transpose(y) : y;
+    // One straight-line path for all four directions (the lanes of a warp hold all of them, so branches would diverge and
+    // every divergent path is issued anyway): masks select the transposed / mirrored board, ONE slide-left, masks undo.
+    const uint64_t mt = 0 - uint64_t(d & 1), mf = 0 - uint64_t((d >> 1) & 1);
+    uint64_t x = b ^ ((b ^ transpose(b)) & mt);
+    x ^= (x ^ flip_h(x)) & mf;
+    uint64_t y = move_left(lut, x, gain, flags);
+    y ^= (y ^ flip_h(y)) & mf;
+    return y ^ ((y ^ transpose(y)) & mt);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -323,8 +328,7 @@ __host__ __device__ __forceinline__ uint32_t spawn_apply(uint64_t &b, uint32_t r
 __host__ __device__ __forceinline__ void spawn_apply_nonempty(uint64_t &b, uint32_t r_tile, uint32_t r_pos)
 {
     const uint64_t z = zero_nibbles(b);
-    const int m = popc64(z);
-    if (m == 0) return;
+    const int m = popc64(z);                                          // (a full board falls through: hit = 0)
     const uint32_t k = umulhi32(r_pos, uint32_t(m));
     const uint64_t prefix = z * 0x1111111111111111ULL;
     const uint64_t want = uint64_t(uint32_t(m) - k) * 0x1111111111111111ULL;
