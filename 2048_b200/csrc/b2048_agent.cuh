@@ -428,7 +428,7 @@ struct LutShared {
     }
 };
 
-constexpr int LUT_SMEM_BYTES = 65536 * 2 + 65536;
+constexpr int LUT_SMEM_BYTES = 65536 * 2 + 65536 + 256 * 4;        // lines u16, merge codes u8, score of a code byte u32
 
 __device__ __forceinline__ void stage_lut_shared(const uint32_t *__restrict__ lut, unsigned char *smem)
 {
@@ -440,6 +440,9 @@ __device__ __forceinline__ void stage_lut_shared(const uint32_t *__restrict__ lu
         reinterpret_cast<uint32_t *>(scode)[q] = ((e.x >> 16) & 0xFFu) | (((e.y >> 16) & 0xFFu) << 8) |
                                                  (((e.z >> 16) & 0xFFu) << 16) | (((e.w >> 16) & 0xFFu) << 24);
     }
+    // merge score of a code byte (exponents a | b << 4): 2^(a+1) + 2^(b+1), 0 for "no merge"
+    uint32_t *sscore = reinterpret_cast<uint32_t *>(smem + 65536 * 3);
+    for (int q = threadIdx.x; q < 256; q += blockDim.x) sscore[q] = ((2u << (q & 15)) & ~2u) + ((2u << (q >> 4)) & ~2u);
     __syncthreads();
 }
 
@@ -675,12 +678,10 @@ __device__ __forceinline__ bool spec_overflow(uint32_t codes)        // some mer
     return (t & 0x11111111u) != 0;
 }
 
-__device__ __forceinline__ uint32_t spec_gain(uint32_t codes)        // score += 2^(x+1) per merge (game_logic.py:33)
+// score += 2^(x+1) per merge (game_logic.py:33): four lookups in the 256-entry score table of the code bytes
+__device__ __forceinline__ uint32_t spec_gain(const uint32_t *__restrict__ sscore, uint32_t codes)
 {
-    uint32_t sc = 0;
-#pragma unroll
-    for (int q = 0; q < 8; q++) sc += (2u << ((codes >> (4 * q)) & 15u)) & ~2u;
-    return sc;
+    return sscore[codes & 0xFFu] + sscore[(codes >> 8) & 0xFFu] + sscore[(codes >> 16) & 0xFFu] + sscore[codes >> 24];
 }
 
 constexpr int SPEC_THREADS = 128;
@@ -773,7 +774,8 @@ greedy_spec_kernel(const float *__restrict__ w, const uint32_t *__restrict__ lut
         });
         // ---- in the shadow of the gathers: the spawn words of the two moves after these, the merge scores
         const Philox4 p3 = spawn_words(g.seed, id, odo + 3u, 0u), p4 = spawn_words(g.seed, id, odo + 4u, 0u);
-        const uint32_t g1 = spec_gain(codes1), g2 = spec_gain(codes2);
+        const uint32_t *sscore = reinterpret_cast<const uint32_t *>(lut_smem + 65536 * 3);
+        const uint32_t g1 = spec_gain(sscore, codes1), g2 = spec_gain(sscore, codes2);
         const uint32_t f1 = ovf1 ? 2u : 0u, f2 = spec_overflow(codes2) ? 2u : 0u;
         // ---- first move: argmax over d among the lanes (d, 0) (xor 4, xor 8), then everybody reads lane (0, 0)
         float s1 = 0.0f;
