@@ -1630,6 +1630,9 @@ __device__ __forceinline__ void grid_arrive(uint32_t *bar, uint32_t &target)
     }
 }
 
+// Besides the formal acquire below, every datum another CTA may have written before the barrier -- weights, accumulators,
+// counts, hot table, key lists, staged updates -- is read after it with ld.cg / an atomic, i.e. at L2; ld.ca /
+// ld.global.nc are used only for the row LUT, which nobody writes, and for the CTA's own game slots.
 // Returns false when the launch is dead: a wait of 2^25 polls (seconds) can only be a lost CTA.  The CTA that times out
 // raises g.counters[B2048_CTR_FAULT]; every other CTA sees the flag within 2^12 polls and leaves too, so the launch
 // ends instead of hanging the device, and the host finds the fault in the counters it reads anyway (engine raises).
@@ -1647,6 +1650,11 @@ __device__ __forceinline__ bool grid_wait(const uint32_t *bar, uint32_t target, 
             }
         }
         if (dead) atomicExch(reinterpret_cast<unsigned long long *>(fault), 1ULL);
+        // the acquire of the PTX memory model: one more read of the counter after the relaxed polling, synchronising with
+        // the arrivals' red.release.gpu (thread 0 acquires, the bar.sync below extends it to the CTA).  It compiles to
+        // LDG.STRONG.GPU + CCTL.IVALL, i.e. it drops the SM's L1 once per barrier; measured cost 1 % at the headline shape
+        // (12.02 -> 12.14 us per lock-step), 0.1 % elsewhere (profiles/r02_barrier_acquire.txt).
+        asm volatile("{ .reg .u32 seen; ld.acquire.gpu.global.u32 seen, [%0]; }" ::"l"(bar) : "memory");
         s_dead = dead;
     }
     __syncthreads();
