@@ -580,6 +580,30 @@ def test_argument_errors(eng):
     assert L.b2048_td_run(4, engine.dptr(w), None, engine.dptr(ctx.lut), C.byref(games.c), C.c_float(0.25), 128, 5,
                           engine.dptr(tr.upd_board), engine.dptr(tr.upd_dw), engine.dptr(tr.work), tr.work.numel(),
                           None) == -1                                                               # unknown mode bit
+    # multi-GPU exchange entry points
+    z = ctx.zeros(64, torch.float32)
+    assert L.b2048_delta_pack_bits(engine.dptr(z), engine.dptr(z), None, engine.dptr(z), 64, None) == -1
+    assert L.b2048_delta_pack_bits(None, None, None, None, 0, None) == 0
+    assert L.b2048_delta_apply_bits(engine.dptr(z), engine.dptr(z), engine.dptr(z), engine.dptr(z), 0, 64, None) == -1   # world 0
+    pz = cabi.Peers()
+    assert L.b2048_td_run_peers(4, engine.dptr(w), engine.dptr(ctx.lut), C.byref(games.c), C.c_float(0.25), 2, 5,
+                                engine.dptr(tr.upd_board), engine.dptr(tr.upd_dw), engine.dptr(tr.work), tr.work.numel(),
+                                C.byref(pz), 4, 0, 1, None) == -1                                     # world 0
+    fl = ctx.zeros(cabi.PEER_FLAG_WORDS, torch.int32)
+    ws = w.clone()
+    pz.w[0], pz.w_sync[0], pz.flags[0], pz.world, pz.rank = w.data_ptr(), ws.data_ptr(), fl.data_ptr(), 1, 0
+    assert L.b2048_td_run_peers(4, engine.dptr(w), engine.dptr(ctx.lut), C.byref(games.c), C.c_float(0.25), 2, 5,
+                                engine.dptr(tr.upd_board), engine.dptr(tr.upd_dw), engine.dptr(tr.work), tr.work.numel(),
+                                C.byref(pz), 4, 4, 1, None) == -1                                     # since_sync >= sync_every
+    assert L.b2048_td_run_peers(4, engine.dptr(ws), engine.dptr(ctx.lut), C.byref(games.c), C.c_float(0.25), 2, 5,
+                                engine.dptr(tr.upd_board), engine.dptr(tr.upd_dw), engine.dptr(tr.work), tr.work.numel(),
+                                C.byref(pz), 4, 0, 1, None) == -1                                     # weights != peers.w[rank]
+    # world 1 through the persistent launch: 5 lock-steps, one exchange after the 4th (w_sync catches up with w there)
+    assert L.b2048_td_run_peers(4, engine.dptr(w), engine.dptr(ctx.lut), C.byref(games.c), C.c_float(0.25), 2, 5,
+                                engine.dptr(tr.upd_board), engine.dptr(tr.upd_dw), engine.dptr(tr.work), tr.work.numel(),
+                                C.byref(pz), 4, 0, 1, engine.cur_stream()) == 0
+    torch.cuda.synchronize()
+    assert int(fl[cabi.PEER_FAULT].item()) == 0 and bool((w != ws).any()) and games.read_counters()["updates"] > 0
     # look-ahead entry points
     assert L.b2048_look_forward(4, engine.dptr(w), engine.dptr(ctx.lut), None, None, None, None, 0, 5, 1, 6, 0, None, None) == -1
     assert L.b2048_look_forward(4, engine.dptr(w), engine.dptr(ctx.lut), None, None, None, None, 0, 2, 5, 6, 0, None, None) == -1
