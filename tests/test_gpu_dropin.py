@@ -91,6 +91,15 @@ def test_agent_evaluate_update_match_reference_pickle(mods):
     after = np.concatenate([a.reshape(-1) for a in agent.list_to_np()])
     assert abs((after - before).sum() - 0.5 * 8 * 24) < 1e-3 and 0 < np.count_nonzero(after != before) <= 8 * 24
     assert abs(agent.evaluate(row) - (probe["values32"][0] + (after - before)[rl.f_2(row) + 256 * np.arange(24)].sum())) < 1e-4
+    # the reference's `agent.weights[i][f]` (list of lists while the agent is live, r_learning.py:136-164) keeps working as
+    # a read-only per-table view of the device buffer
+    view = agent.weights
+    assert len(view) == 24 and view[3].shape == (256,) and view[-1].dtype == np.float32
+    f = rl.f_2(row)
+    assert abs(sum(float(view[i][f[i]]) for i in range(24)) - agent.evaluate(row)) < 1e-4
+    assert np.array_equal(np.concatenate(list(view)), after) and np.array_equal(view[2:4][1], view[3])
+    with pytest.raises(ValueError):
+        view[0][0] = 1.0
 
 
 def test_episode_returns_a_replayable_game(mods, fx):
