@@ -664,6 +664,12 @@ def greedy_bench(D, ctx, args, n, first_id, B, wd, steps, warmup, label, sampler
                         "traffic": tr_b * moves / D.world / steps if tr_b else None,
                         "peak_source": how, "bytes_per_move": bpm, "evals_per_move": E,
                         "sector_granular_GBps": value / D.world * (16 + 32 * F * E) / 1e9,
+                        "l2_gather": {"achieved_gathers_per_sec": value / D.world * F * E, "peak_gathers_per_sec": 293e9,
+                                      "frac": value / D.world * F * E / 293e9,
+                                      "peak_source": "profiles/r02_microbench_gather.txt: random 4-byte gathers over an "
+                                                     "L2-resident footprint, 9.4 TB/s of 32-byte sectors (57 G/s = 1.8 TB/s "
+                                                     "when the footprint is the whole 383 MB of n=6 in HBM); a fraction "
+                                                     "above 1 is L1 hits"},
                         "note": "algorithmic bytes = 16 + 4 F E per move; a random 4-byte gather moves a 32-byte sector, "
                                 "sector_granular_GBps counts those; tables of n <= 5 are L2-resident"},
            "cpu_baseline": None}
