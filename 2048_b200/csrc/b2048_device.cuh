@@ -325,15 +325,27 @@ __host__ __device__ __forceinline__ uint32_t spawn_apply(uint64_t &b, uint32_t r
 // 0..j (at most 15, so no nibble overflows); the k-th empty cell in row-major order is the (m - k)-th from the least
 // significant end, i.e. the one empty nibble whose prefix count equals m - k.  Returns nothing (callers that record
 // the spawn use spawn_apply).
+// zero-nibble mask at bit 3 of every nibble (0x8 per empty cell), without shifts: ((x & 7..7) + 7..7) | x has bit 3 set
+// iff the nibble is non-zero, and the add never carries across nibbles.  (The integer-logic pipe, which executes shifts,
+// is the busy one in the sweep; the add runs on the other pipe.)
+__host__ __device__ __forceinline__ uint64_t zero_nibbles_hi(uint64_t x)
+{
+    // on the halves: no carry can cross the 32-bit boundary, so no add-with-carry chain is needed
+    const uint32_t lo = uint32_t(x), hi = uint32_t(x >> 32);
+    const uint32_t zl = ~(((lo & 0x77777777u) + 0x77777777u) | lo) & 0x88888888u;
+    const uint32_t zh = ~(((hi & 0x77777777u) + 0x77777777u) | hi) & 0x88888888u;
+    return (uint64_t(zh) << 32) | zl;
+}
+
 __host__ __device__ __forceinline__ void spawn_apply_nonempty(uint64_t &b, uint32_t r_tile, uint32_t r_pos)
 {
-    const uint64_t z = zero_nibbles(b);
-    const int m = popc64(z);                                          // (a full board falls through: hit = 0)
+    const uint64_t z8 = zero_nibbles_hi(b);
+    const int m = popc64(z8);                                         // (a full board falls through: hit = 0)
     const uint32_t k = umulhi32(r_pos, uint32_t(m));
-    const uint64_t prefix = z * 0x1111111111111111ULL;
+    const uint64_t prefix = (z8 >> 3) * 0x1111111111111111ULL;
     const uint64_t want = uint64_t(uint32_t(m) - k) * 0x1111111111111111ULL;
-    const uint64_t hit = zero_nibbles(prefix ^ want) & z;             // one bit: bit 4j of the chosen nibble j
-    b |= hit * uint64_t(umulhi32(r_tile, 10u) == 0 ? 2u : 1u);       // (a multiply: the shifter pipe is the busy one)
+    const uint64_t hit8 = zero_nibbles_hi(prefix ^ want) & z8;        // one bit: bit 4j + 3 of the chosen nibble j
+    b |= (hit8 >> 3) * uint64_t(umulhi32(r_tile, 10u) == 0 ? 2u : 1u);   // (a multiply: the shifter pipe is the busy one)
 }
 
 // BASELINE config 5 (b2048_sweep) draws ONE Philox block per board, counter (index_lo, index_hi, 0, purpose 1), and
