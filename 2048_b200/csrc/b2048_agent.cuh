@@ -1687,7 +1687,7 @@ __device__ __forceinline__ bool peer_sync_in_kernel(const PeerSync &ps, uint32_t
     }
     if (int(threadIdx.x) < W && !wait_epoch(mine + B2048_PEER_ARRIVE + threadIdx.x, epoch)) s_ok = 0;
     __syncthreads();
-    if (s_ok) peer_reduce_slice(P, ps.count, int64_t(blockIdx.x) * blockDim.x + threadIdx.x, int64_t(gridDim.x) * blockDim.x);
+    if (s_ok) peer_reduce_slice_scalar(P, ps.count, int64_t(blockIdx.x) * blockDim.x + threadIdx.x, int64_t(gridDim.x) * blockDim.x);
     __syncthreads();
     if (threadIdx.x == 0) __threadfence_system();             // the CTA's remote stores are performed (cumulative)
     if (!grid_barrier(bar, bar_target, fault)) return false;  // ... and every other CTA's of this rank

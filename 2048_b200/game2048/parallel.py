@@ -10,8 +10,9 @@ Two implementations of the exchange (same formula; each leaves the replicas bit-
           mapped into every process; rank r reduces slice r from remote loads and stores the result into every replica.
           No NCCL call, no message buffers.  One stand-alone kernel per sync (b2048_sync_peers: 40 us at n=4 on
           2 GPUs), or with `fused=True` INSIDE the persistent training launch (b2048_td_run_peers: run(S) is one kernel
-          per rank however many syncs fall into it; 28 us per sync, but that kernel variant runs its lock-steps 3 %
-          slower today, so it is not the default).
+          per rank however many syncs fall into it; bit-identical results, but measured 2 % slower over a bench step
+          than the stand-alone kernel between launches -- 26.5 vs 26.0 ms per 2,048 lock-steps on 2 GPUs -- so it is
+          not the default).
   "nccl"  b2048_delta_pack_bits -> allreduce(sum) of the float32 deltas + allgather of the one-bit-per-weight
           contributor planes (4.125 bytes per weight on the wire instead of the 8 of a float indicator) ->
           b2048_delta_apply_bits.  The portable path, and the one the CPU tier exercises under gloo.
