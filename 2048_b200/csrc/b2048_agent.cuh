@@ -1826,7 +1826,7 @@ constexpr int PERSIST_TILE = 32;           // FAST path: at most this many slots
 // registers across the barrier and applies / flushes them itself: no lists, no cursors, no global round trip
 // except the weight gathers and the atomics.  Otherwise slots are processed in rounds through the b2048_td_step
 // staging arrays and per-CTA key lists in global memory.
-// SCAN (n <= 5; the launcher's choice for the float modes in the generic layout):
+// SCAN (n <= 5; the launcher's choice in the generic layout):
 // no first-touch bookkeeping at all.  Phase B fires non-returning REDs (1.5 instead of 2.3 LSU cycles per lane), and the
 // apply phase is a dense, coalesced scan of the accumulators by all CTAs (8.9 MB at n = 4: ~60 KB per SM and lock-step),
 // which finds the touched keys by their non-zero contributor count.
@@ -2109,34 +2109,55 @@ td_persist_kernel(PersistBuffers pb, PersistCtrl *ctrl, const uint32_t *__restri
                 else hv = __ldcg(hot2 + hq);
             }
             if (SCAN) {
-                // dense scan of the accumulators, 4 x 16 bytes per thread in flight; a key is touched iff its contributor
+                // dense scan of the accumulators, SB x 16 bytes per thread in flight; a key is touched iff its contributor
                 // count is non-zero (float modes: the .y of its {sum, count} pair; exact modes: cnt[k])
                 constexpr int64_t NWT = table_offset(N, F);
-                constexpr int SB = 4;
+#ifndef B2048_SCAN_BATCH
+#define B2048_SCAN_BATCH 8
+#endif
+                constexpr int SB = B2048_SCAN_BATCH;           // 16-byte loads in flight per thread (the scan is latency-bound)
                 const int64_t gsz = int64_t(gridDim.x) * blockDim.x, g0 = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+                // Two rounds of loads per batch, each with everything in flight: the accumulators, then -- for the units that
+                // hold a touched key -- the old weights (and the exact sums).  Stores are per key: a neighbour in the same
+                // 16-byte unit may be a small-exponent key that the hot-table pass updates at the same time.
                 if (EXACT) {
                     static_assert(NWT % 4 == 0, "cnt is scanned four keys at a time");
+                    constexpr int SE = SB < 4 ? SB : 4;
                     const uint4 *c4 = reinterpret_cast<const uint4 *>(pb.cnt);
-                    for (int64_t q0 = g0; q0 < NWT / 4; q0 += SB * gsz) {
-                        uint4 cv[SB];
+                    for (int64_t q0 = g0; q0 < NWT / 4; q0 += SE * gsz) {
+                        uint4 cv[SE];
 #pragma unroll
-                        for (int a = 0; a < SB; a++) {
+                        for (int a = 0; a < SE; a++) {
                             const int64_t q = q0 + a * gsz;
                             cv[a] = q < NWT / 4 ? __ldcg(c4 + q) : make_uint4(0u, 0u, 0u, 0u);
                         }
+                        ulonglong2 s01[SE], s23[SE];
+                        float4 wv[SE];
 #pragma unroll
-                        for (int a = 0; a < SB; a++) {
-                            const uint32_t cc[4] = {cv[a].x, cv[a].y, cv[a].z, cv[a].w};
+                        for (int a = 0; a < SE; a++)
+                            if (cv[a].x | cv[a].y | cv[a].z | cv[a].w) {
+                                const int64_t k = 4 * (q0 + a * gsz);
+                                s01[a] = __ldcg(reinterpret_cast<const ulonglong2 *>(accq + k));
+                                s23[a] = __ldcg(reinterpret_cast<const ulonglong2 *>(accq + k + 2));
+                                wv[a] = __ldcg(reinterpret_cast<const float4 *>(pb.w + k));
+                            }
 #pragma unroll
-                            for (int e = 0; e < 4; e++)
-                                if (cc[e]) {
-                                    const uint32_t k = uint32_t(4 * (q0 + a * gsz) + e);
-                                    const float u = update_value<true, MEAN>((long long)__ldcg(accq + k), 0.0f, float(cc[e]));
-                                    __stcg(accq + k, 0ULL);
-                                    __stcg(pb.cnt + k, 0u);
-                                    add_weight(pb.w, pb.delta, k, u);
-                                }
-                        }
+                        for (int a = 0; a < SE; a++)
+                            if (cv[a].x | cv[a].y | cv[a].z | cv[a].w) {
+                                const uint32_t k0 = uint32_t(4 * (q0 + a * gsz));
+                                const uint32_t cc[4] = {cv[a].x, cv[a].y, cv[a].z, cv[a].w};
+                                const unsigned long long qq[4] = {s01[a].x, s01[a].y, s23[a].x, s23[a].y};
+                                const float ww[4] = {wv[a].x, wv[a].y, wv[a].z, wv[a].w};
+#pragma unroll
+                                for (int e = 0; e < 4; e++)
+                                    if (cc[e]) {
+                                        const float u = update_value<true, MEAN>((long long)qq[e], 0.0f, float(cc[e]));
+                                        __stcg(accq + k0 + e, 0ULL);
+                                        __stcg(pb.cnt + k0 + e, 0u);
+                                        __stcg(pb.w + k0 + e, __fadd_rn(ww[e], u));
+                                        if (pb.delta) __stcg(pb.delta + k0 + e, __fadd_rn(__ldcg(pb.delta + k0 + e), u));
+                                    }
+                            }
                     }
                 } else {
                     static_assert(NWT % 2 == 0, "the {sum, count} pairs are scanned two keys at a time");
@@ -2148,16 +2169,25 @@ td_persist_kernel(PersistBuffers pb, PersistCtrl *ctrl, const uint32_t *__restri
                             const int64_t q = q0 + a * gsz;
                             v[a] = q < NWT / 2 ? __ldcg(a4 + q) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                         }
+                        float2 wv[SB];
+#pragma unroll
+                        for (int a = 0; a < SB; a++)
+                            if (v[a].y != 0.0f || v[a].w != 0.0f)
+                                wv[a] = __ldcg(reinterpret_cast<const float2 *>(pb.w + 2 * (q0 + a * gsz)));
 #pragma unroll
                         for (int a = 0; a < SB; a++) {
                             const uint32_t k = uint32_t(2 * (q0 + a * gsz));
                             if (v[a].y != 0.0f) {
+                                const float u = update_value<false, MEAN>(0, v[a].x, v[a].y);
                                 __stcg(acc2 + k, make_float2(0.0f, 0.0f));
-                                add_weight(pb.w, pb.delta, k, update_value<false, MEAN>(0, v[a].x, v[a].y));
+                                __stcg(pb.w + k, __fadd_rn(wv[a].x, u));
+                                if (pb.delta) __stcg(pb.delta + k, __fadd_rn(__ldcg(pb.delta + k), u));
                             }
                             if (v[a].w != 0.0f) {
+                                const float u = update_value<false, MEAN>(0, v[a].z, v[a].w);
                                 __stcg(acc2 + k + 1, make_float2(0.0f, 0.0f));
-                                add_weight(pb.w, pb.delta, k + 1, update_value<false, MEAN>(0, v[a].z, v[a].w));
+                                __stcg(pb.w + k + 1, __fadd_rn(wv[a].y, u));
+                                if (pb.delta) __stcg(pb.delta + k + 1, __fadd_rn(__ldcg(pb.delta + k + 1), u));
                             }
                         }
                     }
@@ -2443,10 +2473,10 @@ int td_run_persistent(float *weights, float *delta, const uint32_t *lut, const b
     const bool with_peers = ps.sync_every > 0;
     // FAST: one phase-B round per lock-step, state in registers, staging and key list in shared memory
     const bool fast = spc <= PERSIST_THREADS / num_feat(N) && spc <= PERSIST_TILE && !(mode & B2048_RUN_GENERIC);
-    // scanning apply: float modes in the generic layout (measured, profiles/r02_td_scan_vs_lists.txt: 11-49 % faster there;
-    // the one-round register layout keeps its lists, 5 % faster at 4,096 games; exact modes: the two-array scan loses
-    // 4-8 %), or when forced either way (the parity tests run both)
-    bool scan = N <= 5 && !det && !fast;
+    // scanning apply: every mode in the generic layout (measured, profiles/r02_td_scan_vs_lists.txt: float modes 15-50 %
+    // faster there, exact modes 1-17 %; the one-round register layout keeps its lists, 5 % faster at 4,096 games), or
+    // when forced either way (the parity tests run both)
+    bool scan = N <= 5 && !fast;
     if (mode & B2048_RUN_SCAN) scan = N <= 5;
     if (mode & B2048_RUN_LISTS) scan = false;
     const int rc = fast ? (with_peers ? launch_persist_scan<N, true, true>(scan, det, mean, grid, st, args)

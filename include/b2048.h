@@ -247,8 +247,8 @@ int b2048_td_phase_a(int n, const float *weights, const uint32_t *lut, const b20
 /* mode | B2048_RUN_GENERIC: the persistent kernel in its generic slot layout (rounds over the staging arrays and per-CTA
  * key lists) even where the one-round register layout would fit; same results, used by the parity tests */
 #define B2048_RUN_GENERIC 16
-/* the apply phase of the persistent kernel: a dense scan of the accumulators (default for the ATOMIC modes when the
- * batch needs the generic slot layout; n <= 5) or the lists of first-touched keys.  mode | B2048_RUN_SCAN /
+/* the apply phase of the persistent kernel: a dense scan of the accumulators (default when the batch needs the generic slot
+ * layout; n <= 5) or the lists of first-touched keys.  mode | B2048_RUN_SCAN /
  * B2048_RUN_LISTS force one of them (same results; the parity tests run both). */
 #define B2048_RUN_SCAN 32
 #define B2048_RUN_LISTS 64
