@@ -1799,6 +1799,7 @@ struct PersistBuffers {
     uint32_t *lists;        // per-CTA key lists, list_cap keys each
     void *hot;              // float2[NS] | int64[NS] followed by u32[NS]
     int64_t list_cap;
+    float *tune;            // [grid] slots per kilo-cycle each CTA sustained in the previous launch (0 = not measured yet)
 };
 
 template <bool EXACT, bool MEAN>
@@ -1849,8 +1850,45 @@ td_persist_kernel(PersistBuffers pb, PersistCtrl *ctrl, const uint32_t *__restri
     __shared__ uint64_t s_img[FAST ? PERSIST_TILE * 8 : 1];
     __shared__ float s_dw[FAST ? PERSIST_TILE : 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const int64_t slot0 = int64_t(blockIdx.x) * spc;
-    const int nslots = int(g.B - slot0 < spc ? (g.B - slot0 > 0 ? g.B - slot0 : 0) : spc);
+    int64_t slot0 = int64_t(blockIdx.x) * spc;
+    int nslots = int(g.B - slot0 < spc ? (g.B - slot0 > 0 ? g.B - slot0 : 0) : spc);
+    // Self-tuning partition (generic layout with the scanning apply: slots live in global memory and nothing per CTA is
+    // sized by its slot count).  SMs do not sustain the same atomic / gather rate -- with 65,536 games at n = 5 the slowest
+    // CTA needs 1.5x the cycles of the fastest, always the same ones (far from the L2 slices that hold the accumulators) --
+    // and the grid barrier waits for the slowest.  Every launch leaves each CTA's measured slots per kilo-cycle in the
+    // workspace; the next launch splits the slots in proportion (all CTAs read the same table before anyone rewrites it).
+    constexpr bool TUNE = !FAST && SCAN;
+    __shared__ long long s_part[2];
+    if (TUNE && pb.tune) {
+        if (threadIdx.x == 0) {
+            double total = 0.0, before = 0.0, mine = 0.0, mean = 0.0;
+            bool known = true;
+            for (unsigned t = 0; t < gridDim.x; t++) {
+                const float r = __ldcg(pb.tune + t);
+                known = known && r > 0.0f;
+                mean += r;
+            }
+            mean /= double(gridDim.x);
+            for (unsigned t = 0; known && t < gridDim.x; t++) {      // clamped to 0.6 .. 1.6 of the mean rate
+                double r = __ldcg(pb.tune + t);
+                r = r < 0.6 * mean ? 0.6 * mean : r > 1.6 * mean ? 1.6 * mean : r;
+                total += r;
+                if (t < blockIdx.x) before += r;
+                if (t == blockIdx.x) mine = r;
+            }
+            long long lo = slot0, hi = slot0 + nslots;
+            if (known) {                                   // identical arithmetic in every CTA: the ranges tile [0, B)
+                lo = (long long)(double(g.B) * (before / total));
+                hi = blockIdx.x + 1 == gridDim.x ? (long long)g.B : (long long)(double(g.B) * ((before + mine) / total));
+            }
+            s_part[0] = lo;
+            s_part[1] = hi;
+        }
+        __syncthreads();
+        slot0 = s_part[0];
+        nslots = int(s_part[1] - s_part[0]);
+    }
+    long long tune_cycles = 0;
     uint32_t *list = pb.lists + int64_t(blockIdx.x) * pb.list_cap;     // generic path only
     float2 *acc2 = reinterpret_cast<float2 *>(pb.acc);
     unsigned long long *accq = reinterpret_cast<unsigned long long *>(pb.acc);
@@ -1899,6 +1937,7 @@ td_persist_kernel(PersistBuffers pb, PersistCtrl *ctrl, const uint32_t *__restri
         long long *tl = (tlog && threadIdx.x == 0 && step >= steps - 16) ?
                         tlog + (int64_t(blockIdx.x) * 16 + (step - (steps - 16))) * 8 : nullptr;
         if (tl) tl[0] = clock64();
+        const long long tune_t0 = (TUNE && threadIdx.x == 0) ? clock64() : 0;
         // ---- phase A: 4 lanes per slot, 8 slots per warp
         if (FAST) {
             // lane d stages images d and 4 + d (d4_image order).  Except in the DIRECT mode the hand-over to phase B
@@ -2072,6 +2111,7 @@ td_persist_kernel(PersistBuffers pb, PersistCtrl *ctrl, const uint32_t *__restri
             }
         }
         if (tl) tl[3] = clock64();
+        if (TUNE && threadIdx.x == 0) tune_cycles += clock64() - tune_t0;
         grid_arrive(&ctrl->bar, bar_target);                  // every contribution of the step has landed
         if (DIRECT && PREP && a_warp) move_prepare<N>(L, st.board, a_dir, prep);   // W_{t+1} is complete after this one
         // FAST apply, the half that does not depend on other CTAs, done while waiting: which keys this thread
@@ -2306,6 +2346,14 @@ td_persist_kernel(PersistBuffers pb, PersistCtrl *ctrl, const uint32_t *__restri
         }
     }
     if (FAST && a_in && a_dir == 0 && st_dirty) slot_store(g, slot0 + a_slot, st);
+    if (TUNE && pb.tune && threadIdx.x == 0 && tune_cycles > 0 && nslots > 0) {
+        // slots per kilo-cycle of this launch, averaged with the previous figure (all CTAs are past the last barrier of
+        // the launch when the first of them gets here, so nobody still reads the old table)
+        float rate = float(double(nslots) * double(steps) * 1000.0 / double(tune_cycles));
+        const float old = __ldcg(pb.tune + blockIdx.x);
+        if (old > 0.0f) rate = 0.5f * (rate + old);
+        __stcg(pb.tune + blockIdx.x, rate);
+    }
     flush_counters(g.counters, c);
     if (threadIdx.x == 0) {
         __threadfence();
@@ -2455,7 +2503,9 @@ int td_run_persistent(float *weights, float *delta, const uint32_t *lut, const b
     const int grid = int(cdiv(B, spc));
     unsigned char *base = reinterpret_cast<unsigned char *>(work);
     PersistBuffers pb{weights, delta, base + L.acc, reinterpret_cast<uint32_t *>(base + L.cnt),
-                      reinterpret_cast<uint32_t *>(base + L.lists), base + L.hot, spc * 8 * num_feat(N)};
+                      reinterpret_cast<uint32_t *>(base + L.lists), base + L.hot, spc * 8 * num_feat(N),
+                      // (measured: +3 % from 32,768 games up, nothing to gain below ~128 slots per CTA)
+                      ((mode & B2048_RUN_EVEN) || spc < 128) ? nullptr : reinterpret_cast<float *>(base + L.tune)};
     PersistCtrl *ctrl = reinterpret_cast<PersistCtrl *>(base + L.ctrl);
     b2048_games_t games = *g;
     int spc_i = int(spc);

@@ -14,7 +14,7 @@ namespace {
 using namespace b2048;
 
 constexpr unsigned FULL = 0xFFFFFFFFu;
-constexpr int B2048_RUN_LAYOUT = B2048_RUN_GENERIC | B2048_RUN_SCAN | B2048_RUN_LISTS;   // layout hints of b2048_td_run
+constexpr int B2048_RUN_LAYOUT = B2048_RUN_GENERIC | B2048_RUN_SCAN | B2048_RUN_LISTS | B2048_RUN_EVEN;   // layout hints of b2048_td_run
 
 inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
@@ -76,7 +76,7 @@ inline int key_bits(int n)
 struct WorkLayout {
     int64_t M, nw;      // contributions, weights
     int nblocks;        // sort tiles
-    size_t acc, cnt, touched, ctrl, keys_a, keys_b, vals_a, vals_b, hist, lists, hot, total;
+    size_t acc, cnt, touched, ctrl, keys_a, keys_b, vals_a, vals_b, hist, lists, hot, tune, total;
 };
 
 inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
@@ -107,6 +107,7 @@ inline WorkLayout work_layout(int n, int64_t m, int mode)
     // persistent trainer: per-CTA key lists, entries_per_CTA * 8F keys each (PERSIST_MAX_GRID CTAs at most)
     L.lists = o; o += align256(size_t(m + 4 * PERSIST_MAX_GRID) * 8 * num_feat(n) * 4);
     L.hot = o; o += align256(size_t(10752) * 12);                    // dense table of the small-exponent keys (<= 10,625)
+    L.tune = o; o += align256(size_t(PERSIST_MAX_GRID) * 4);         // per-CTA slots per kilo-cycle of the previous launch
     L.total = o;
     return L;
 }

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(os.path.dirname(_HERE), "libb2048.so")
 
 UPD_ATOMIC, UPD_DETERMINISTIC, UPD_SUM, UPD_MEAN, UPD_SORTED, RUN_STEPWISE, RUN_GENERIC = 0, 1, 0, 2, 4, 8, 16
-RUN_SCAN, RUN_LISTS = 32, 64
+RUN_SCAN, RUN_LISTS, RUN_EVEN = 32, 64, 128
 F_HAVE_STATE, F_DONE, F_OVERFLOW = 1, 2, 4
 (CTR_MOVES, CTR_EVALS, CTR_UPDATES, CTR_FINISHED, CTR_SCORE_SUM, CTR_MOVES_SUM, CTR_OVERFLOW, CTR_ACTIVE,
  CTR_LOG, CTR_QUEUE, CTR_FAULT) = range(11)

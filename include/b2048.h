@@ -252,6 +252,11 @@ int b2048_td_phase_a(int n, const float *weights, const uint32_t *lut, const b20
  * B2048_RUN_LISTS force one of them (same results; the parity tests run both). */
 #define B2048_RUN_SCAN 32
 #define B2048_RUN_LISTS 64
+/* In the generic layout with the scanning apply the persistent kernel splits the slots over its CTAs in proportion to the
+ * slots per kilo-cycle each CTA sustained in the PREVIOUS launch on this workspace (from 128 slots per CTA up; SMs differ
+ * by up to 1.5x in the atomic rate they sustain; the first launch on a zeroed workspace splits evenly).  Results do not depend on the split
+ * (bit-identical in the DETERMINISTIC modes).  mode | B2048_RUN_EVEN keeps the even split. */
+#define B2048_RUN_EVEN 128
 /* number of kernel launches b2048_td_run(n, B slots, mode, steps) enqueues on this device (1 = persistent) */
 int64_t b2048_td_run_launches(int n, int64_t B, int mode, int steps);
 int b2048_td_run(int n, float *weights, float *delta, const uint32_t *lut, const b2048_games_t *g, float alpha,

@@ -31,7 +31,7 @@ ctx = engine.Context.get()
 mode = (cabi.UPD_DETERMINISTIC if a.mode == "deterministic" else 0) | (cabi.UPD_MEAN if a.rule == "mean" else 0) | \
        (cabi.UPD_SORTED if a.sorted else 0)
 for word in a.layout.split("+"):
-    mode |= {"": 0, "generic": cabi.RUN_GENERIC, "scan": cabi.RUN_SCAN, "lists": cabi.RUN_LISTS}[word]
+    mode |= {"": 0, "generic": cabi.RUN_GENERIC, "scan": cabi.RUN_SCAN, "lists": cabi.RUN_LISTS, "even": cabi.RUN_EVEN}[word]
 wd = ctx.to_device(bench.seeded_weights(a.n))
 games = engine.GameBatch(a.games, seed=0, ctx=ctx).init()
 tr = engine.TDTrainer(ctx, a.n, wd, games, 0.25 if a.rule == "mean" else 0.25 / a.games, mode)

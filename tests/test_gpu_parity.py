@@ -426,7 +426,8 @@ def test_td_lockstep_deterministic_bit_exact(eng, orc, fx, n, B):
                                              (6, 4096, 12, None), (6, 300, 40, "generic"),
                                              # both apply phases forced where the launcher would pick the other one
                                              (4, 4096, 40, "lists"), (4, 1000, 80, "scan"), (4, 64, 100, "generic+scan"),
-                                             (5, 6000, 30, "scan"), (3, 2000, 40, "scan"), (2, 500, 60, "scan")])
+                                             (5, 6000, 30, "scan"), (3, 2000, 40, "scan"), (2, 500, 60, "scan"),
+                                             (4, 20000, 24, "even"), (4, 20000, 24, None)])
 def test_td_persistent_paths_bit_exact(eng, orc, fx, monkeypatch, n, B, steps, force):
     """b2048_td_run's persistent kernel gives the oracle's bits in the deterministic modes in both slot layouts:
     one phase-B round per CTA with the state in registers ((6, 700), (4, 3000), (3, 1000), (2, 2000), (4, 8)), and
@@ -435,7 +436,8 @@ def test_td_persistent_paths_bit_exact(eng, orc, fx, monkeypatch, n, B, steps, f
     ctx, engine, cabi = eng
     layout = 0
     for word in (force or "").split("+"):
-        layout |= {"": 0, "generic": cabi.RUN_GENERIC, "scan": cabi.RUN_SCAN, "lists": cabi.RUN_LISTS}[word]
+        layout |= {"": 0, "generic": cabi.RUN_GENERIC, "scan": cabi.RUN_SCAN, "lists": cabi.RUN_LISTS,
+                   "even": cabi.RUN_EVEN}[word]
     for rule, mode, alpha in ((4, cabi.UPD_DETERMINISTIC | cabi.UPD_MEAN, 0.25),
                               (3, cabi.UPD_DETERMINISTIC | cabi.UPD_SUM, 0.25 / B)):
         w0 = fx.flat(fx.init_weights32(n, 41)).astype(np.float32)
@@ -577,7 +579,7 @@ def test_argument_errors(eng):
     tr = engine.TDTrainer(ctx, 4, w, games, 0.25, cabi.UPD_ATOMIC | cabi.UPD_MEAN)
     assert L.b2048_td_run(4, engine.dptr(w), None, engine.dptr(ctx.lut), C.byref(games.c), C.c_float(0.25), 2, 5,
                           engine.dptr(tr.upd_board), engine.dptr(tr.upd_dw), None, 0, None) == -3   # no workspace
-    assert L.b2048_td_run(4, engine.dptr(w), None, engine.dptr(ctx.lut), C.byref(games.c), C.c_float(0.25), 128, 5,
+    assert L.b2048_td_run(4, engine.dptr(w), None, engine.dptr(ctx.lut), C.byref(games.c), C.c_float(0.25), 256, 5,
                           engine.dptr(tr.upd_board), engine.dptr(tr.upd_dw), engine.dptr(tr.work), tr.work.numel(),
                           None) == -1                                                               # unknown mode bit
     # multi-GPU exchange entry points
