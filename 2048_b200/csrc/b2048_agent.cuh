@@ -478,9 +478,11 @@ __device__ __forceinline__ void best_move_finish(const float *__restrict__ w, co
     int bd = valid ? d : 4;                           // invalid lanes never win ties
 #pragma unroll
     for (int off = 1; off < 4; off <<= 1) {
-        float ov = __shfl_xor_sync(FULL, bv, off, 4);
-        int od = __shfl_xor_sync(FULL, bd, off, 4);
-        if (od < 4 && (bd == 4 || ov > bv || (ov == bv && od < bd))) { bv = ov; bd = od; }
+        const float ov = __shfl_xor_sync(FULL, bv, off, 4);
+        const int od = __shfl_xor_sync(FULL, bd, off, 4);
+        const bool take = (od < 4) & ((bd == 4) | (ov > bv) | ((ov == bv) & (od < bd)));   // selects, no divergent branch
+        bv = take ? ov : bv;
+        bd = take ? od : bd;
     }
     n_valid = __popc(__ballot_sync(FULL, valid) >> ((threadIdx.x & 31) & ~3) & 0xFu);
     const int src = bd & 3;
