@@ -663,6 +663,9 @@ int b2048_td_run(int n, float *weights, float *delta, const uint32_t *lut, const
 {
     if (steps < 0 || (mode & ~(7 | B2048_RUN_STEPWISE | B2048_RUN_LAYOUT))) return B2048_EINVAL;
     if (!games_ok(g) || num_feat(n) < 0 || !weights || !lut || !upd_board || !upd_dw) return B2048_EINVAL;
+    if ((reinterpret_cast<uintptr_t>(weights) & 15) || (delta && (reinterpret_cast<uintptr_t>(delta) & 15)) ||
+        (reinterpret_cast<uintptr_t>(work) & 15))
+        return B2048_EINVAL;                                       // the apply phase uses 16-byte vector loads
     if (steps == 0 || g->B == 0) return 0;
     const bool stepwise = mode & (B2048_RUN_STEPWISE | B2048_UPD_SORTED);
     const int layout = mode & B2048_RUN_LAYOUT;
@@ -692,6 +695,7 @@ int b2048_td_run_peers(int n, float *weights, const uint32_t *lut, const b2048_g
     for (int q = 0; q < peers->world; q++)
         if (!peers->w[q] || !peers->w_sync[q] || !peers->flags[q]) return B2048_EINVAL;
     if (peers->w[peers->rank] != weights) return B2048_EINVAL;      // the trained buffer must be the mapped one
+    if ((reinterpret_cast<uintptr_t>(weights) & 15) || (reinterpret_cast<uintptr_t>(work) & 15)) return B2048_EINVAL;
     if (steps == 0) return 0;
     if (g->B == 0 || !cooperative_ok()) return B2048_ENOTSUP;       // every rank needs the persistent launch
     PeerSync ps{};

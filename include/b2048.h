@@ -240,7 +240,8 @@ int b2048_td_phase_a(int n, const float *weights, const uint32_t *lut, const b20
                      b2048_stream_t stream);
 /* `steps` lock-steps with no host work in between.  Default: ONE cooperative launch of a persistent kernel
  * (every CTA owns a fixed range of slots; phase A and the accumulation run back to back, a grid barrier, the
- * CTA applies the keys it touched first, a grid barrier) -- same results as `steps` calls of b2048_td_step
+ * CTA applies the keys it touched first, a grid barrier; weights, delta and work must be 16-byte aligned) -- same results as
+ * `steps` calls of b2048_td_step
  * (bit-identical in the DETERMINISTIC modes).  mode | B2048_RUN_STEPWISE (or B2048_UPD_SORTED, or a device
  * without cooperative launch) enqueues b2048_td_step `steps` times instead (3 launches per lock-step). */
 #define B2048_RUN_STEPWISE 8

@@ -582,6 +582,10 @@ def test_argument_errors(eng):
     assert L.b2048_td_run(4, engine.dptr(w), None, engine.dptr(ctx.lut), C.byref(games.c), C.c_float(0.25), 256, 5,
                           engine.dptr(tr.upd_board), engine.dptr(tr.upd_dw), engine.dptr(tr.work), tr.work.numel(),
                           None) == -1                                                               # unknown mode bit
+    wmis = ctx.zeros(cabi.num_weights(4) + 4, torch.float32)[1:]                                    # 4-byte aligned only
+    assert L.b2048_td_run(4, engine.dptr(wmis), None, engine.dptr(ctx.lut), C.byref(games.c), C.c_float(0.25), 2, 5,
+                          engine.dptr(tr.upd_board), engine.dptr(tr.upd_dw), engine.dptr(tr.work), tr.work.numel(),
+                          None) == -1                                                               # 16-byte alignment
     # multi-GPU exchange entry points
     z = ctx.zeros(64, torch.float32)
     assert L.b2048_delta_pack_bits(engine.dptr(z), engine.dptr(z), None, engine.dptr(z), 64, None) == -1
