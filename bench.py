@@ -10,6 +10,7 @@ update = one QAgent.update() equivalent = 8*F weight RMWs).  The `configs` objec
 four configs, each with value / e2e / roofline / cpu_baseline measured in the same invocation:
     configs[0]  greedy n=4, 1,000 seeded games in total from fixed (pre-trained) weights          moves/s, strong
     configs[2]  n=5 TD(0), 65,536 games IN TOTAL split over the N GPUs, weight sync every 64        updates/s, strong
+                (one step = 512 lock-steps = 8 sync periods)
     configs[3]  greedy n=6, 131,072 games per GPU, random-init AND pre-trained weights              moves/s, weak
     configs[4]  board sweep, 16M packed boards per GPU x 4 directions + spawn                       boards/s, weak
 See DESIGN.md "Measurement" for every field.
@@ -796,16 +797,16 @@ def run_configs(D, ctx, args, sampler):
         del wd
         free()
     if want(2):       # ---- configs[2]: n=5, 65,536 games IN TOTAL over the N GPUs, weight sync every 64 lock-steps
-        total, K = 65536, 64
+        total, K, S = 65536, 64, 512                      # one bench step = 512 lock-steps = 8 sync periods
         first, count = parallel.shard(total, D.world, D.rank)
-        r, st = td_bench(D, ctx, args, 5, count, K, ks, kw, cabi.UPD_ATOMIC | cabi.UPD_MEAN, K, first_slot=first,
+        r, st = td_bench(D, ctx, args, 5, count, S, ks, kw, cabi.UPD_ATOMIC | cabi.UPD_MEAN, K, first_slot=first,
                          total_slots=total, sampler=sampler, traffic_key=f"td_persist_n5_B{count}_atomic_mean")
         if r:
             r.update(scaling="strong", total_games=total,
                      config={"workload": f"BASELINE configs[2]: Q_agent n=5 TD(0), {total} games in total sharded over "
                                          f"{D.world} GPU(s) ({count} per GPU), weight sync every {K} lock-steps, "
-                                         "rule=mean, update mode=atomic; one step = one sync period",
-                             "n": 5, "games_per_gpu": count, "lock_steps_per_step": K, "sync_every": K,
+                                         f"rule=mean, update mode=atomic; one step = {S} lock-steps",
+                             "n": 5, "games_per_gpu": count, "lock_steps_per_step": S, "sync_every": K,
                              "l2": "21.2 MB of tables are L2-resident; 256 MiB flush between timed steps"})
             if D.world == 1:
                 r["cpu_baseline"] = cpu_td_baseline(5, total, args.alpha, "mean", min(args.cpu_seconds, 6.0))
