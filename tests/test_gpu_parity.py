@@ -296,6 +296,13 @@ def test_greedy_philox_vs_oracle(eng, orc, fx, n):
     engine.greedy_play(ctx, n, wd, lim, limit_tile=5, step_limit=40)
     ref_l = orc.play_philox(n, w, seed=11, first_id=1000, num=16, limit_tile=5, step_limit=40)
     assert np.array_equal(lim.to_host()["board"], ref_l["boards"])
+    # odd launch budgets and limits (the look-ahead kernel commits up to two moves per iteration and must stop exactly)
+    odd = engine.GameBatch(24, seed=11, ctx=ctx).init(first_id=1000)
+    engine.greedy_play(ctx, n, wd, odd, step_limit=41, chunk=7)
+    ref_o = orc.play_philox(n, w, seed=11, first_id=1000, num=24, step_limit=41)
+    ho = odd.to_host()
+    assert np.array_equal(ho["board"], ref_o["boards"]) and np.array_equal(ho["moves"].astype(np.int32), ref_o["moves"])
+    assert np.array_equal(ho["score"].astype(np.int64), ref_o["scores"])
 
 
 @pytest.mark.parametrize("n", [3, 4, 6])
