@@ -623,3 +623,31 @@ def test_argument_errors(eng):
     assert L.b2048_look_forward(4, engine.dptr(w), engine.dptr(ctx.lut), None, None, None, None, 0, 2, 2, 6, 0, None, None) == 0
     assert L.b2048_expectimax_play(4, engine.dptr(w), engine.dptr(ctx.lut), C.byref(games.c), 4, 0, 100, 9, 1, 6, None, None, 0,
                                    None) == -1
+
+
+@pytest.mark.parametrize("B", [3, 3000])
+def test_greedy_stops_at_the_2_16_escape(eng, orc, fx, B):
+    """A position whose only legal moves would create a 2^16 tile (the reference raises KeyError one move later,
+    game_logic.py:129): both greedy kernels (look-ahead kernel for 3 games, 4-lane kernel for 3,000) stop the game
+    untouched, flag it DONE | OVERFLOW and count it."""
+    ctx, engine, cabi = eng
+    n = 4
+    w, wd = w_dev(ctx, fx, n, 9)
+    row = np.array([[15, 15, 1, 2], [3, 4, 5, 6], [1, 2, 3, 4], [5, 6, 7, 8]], np.int32)
+    start = orc.pack_np(row[None])[0]
+    games = engine.GameBatch(B, seed=1, ctx=ctx).init()
+    games.set_positions(np.full(B, start, dtype=np.uint64))
+    engine.greedy_play(ctx, n, wd, games)
+    h, c = games.to_host(), games.read_counters()
+    assert (h["board"] == start).all() and (h["score"] == 0).all() and (h["moves"] == 0).all()
+    assert (h["flags"] == (cabi.F_DONE | cabi.F_OVERFLOW)).all()
+    assert c["finished"] == B and c["overflow"] == B and c["moves"] == 0 and c["active"] == 0
+    assert h["tile_hist"][16] == B
+    # one move before the escape: [14 14 . .] merges to 2^15 legally, then the game goes on
+    row2 = row.copy()
+    row2[0, :2] = 14
+    g2 = engine.GameBatch(B, seed=1, ctx=ctx).init()
+    g2.set_positions(np.full(B, orc.pack_np(row2[None])[0], dtype=np.uint64))
+    engine.greedy_play(ctx, n, wd, g2, step_limit=1)
+    h2 = g2.to_host()
+    assert (h2["moves"] == 1).all() and (h2["score"] == 1 << 15).all() and not (h2["flags"] & cabi.F_OVERFLOW).any()
