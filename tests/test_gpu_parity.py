@@ -651,3 +651,25 @@ def test_greedy_stops_at_the_2_16_escape(eng, orc, fx, B):
     engine.greedy_play(ctx, n, wd, g2, step_limit=1)
     h2 = g2.to_host()
     assert (h2["moves"] == 1).all() and (h2["score"] == 1 << 15).all() and not (h2["flags"] & cabi.F_OVERFLOW).any()
+
+
+@pytest.mark.parametrize("stepwise", [False, True])
+def test_td_treats_the_2_16_escape_as_the_end_of_the_episode(eng, orc, fx, stepwise):
+    """lock-step TD on a position whose only legal moves would create 2^16: the slot ends its episode there (no update on
+    the first move of an episode: there is no previous afterstate), is counted as overflowed and restarts in place"""
+    ctx, engine, cabi = eng
+    n, B = 4, 8
+    w, wd = w_dev(ctx, fx, n, 9)
+    w_before = wd.clone()
+    row = np.array([[15, 15, 1, 2], [3, 4, 5, 6], [1, 2, 3, 4], [5, 6, 7, 8]], np.int32)
+    games = engine.GameBatch(B, seed=4, ctx=ctx).init()
+    ids0 = games.to_host()["game_id"].copy()
+    games.set_positions(np.full(B, orc.pack_np(row[None])[0], dtype=np.uint64))
+    mode = cabi.UPD_DETERMINISTIC | cabi.UPD_MEAN | (cabi.RUN_STEPWISE if stepwise else 0)
+    engine.TDTrainer(ctx, n, wd, games, 0.25, mode).run(1)
+    h, c = games.to_host(), games.read_counters()
+    assert c["finished"] == B and c["overflow"] == B and c["moves"] == 0 and c["updates"] == 0
+    assert np.array_equal(h["game_id"], ids0 + B) and (h["moves"] == 0).all() and (h["score"] == 0).all()
+    assert (h["flags"] == 0).all()                                      # fresh games
+    assert np.array_equal(h["board"], np.array([orc.pack_np(orc.spawn_initial(4, int(i))[None])[0] for i in h["game_id"]]))
+    assert torch.equal(wd, w_before) and h["tile_hist"][16] == B
