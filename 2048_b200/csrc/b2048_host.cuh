@@ -230,8 +230,9 @@ struct PeerSync {
 
 bool games_ok(const b2048_games_t *g)
 {
-    return g && g->B >= 0 && g->board && g->score && g->moves && g->game_id && g->state && g->old_label && g->flags &&
-           g->counters && g->tile_hist;
+    if (!g || g->B < 0 || !g->counters || !g->tile_hist) return false;
+    if (g->B == 0) return true;                        // an empty batch may carry null slot arrays
+    return g->board && g->score && g->moves && g->game_id && g->state && g->old_label && g->flags;
 }
 
 

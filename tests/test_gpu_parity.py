@@ -673,3 +673,40 @@ def test_td_treats_the_2_16_escape_as_the_end_of_the_episode(eng, orc, fx, stepw
     assert (h["flags"] == 0).all()                                      # fresh games
     assert np.array_equal(h["board"], np.array([orc.pack_np(orc.spawn_initial(4, int(i))[None])[0] for i in h["game_id"]]))
     assert torch.equal(wd, w_before) and h["tile_hist"][16] == B
+
+
+def test_empty_batches_are_no_ops(eng):
+    """m = 0 / B = 0 / steps = 0 / count = 0: every batch entry point returns 0 and touches nothing"""
+    ctx, engine, cabi = eng
+    L = ctx.lib
+    lut, st = engine.dptr(ctx.lut), engine.cur_stream()
+    w = ctx.zeros(cabi.num_weights(2), torch.float32)
+    assert L.b2048_pack(None, None, 0, st) == 0 and L.b2048_unpack(None, None, 0, st) == 0
+    assert L.b2048_move4(lut, None, 0, None, None, None, None, st) == 0
+    assert L.b2048_board_stats(None, 0, None, None, st) == 0
+    assert L.b2048_spawn_philox(None, 0, 1, None, None, None, st) == 0
+    assert L.b2048_spawn_initial(None, 0, 1, 0, 1, st) == 0 and L.b2048_spawn_replay(None, 0, None, None, st) == 0
+    assert L.b2048_sweep(lut, None, 0, 0, 0, None, None, None, None, st) == 0
+    assert L.b2048_features(2, None, 0, None, st) == 0 and L.b2048_evaluate(2, engine.dptr(w), None, 0, None, st) == 0
+    assert L.b2048_td_update(2, engine.dptr(w), None, None, None, 0, 3, None, 0, st) == 0
+    assert L.b2048_look_forward(2, engine.dptr(w), lut, None, None, None, None, 0, 2, 2, 6, 0, None, st) == 0
+    assert L.b2048_delta_pack(None, None, 0, st) == 0 and L.b2048_delta_pack_diff(None, None, None, 0, st) == 0
+    assert L.b2048_delta_apply(None, None, None, None, None, 0, st) == 0
+    assert L.b2048_delta_pack_bits(None, None, None, None, 0, st) == 0
+    assert L.b2048_delta_apply_bits(None, None, None, None, 1, 0, st) == 0
+    empty = engine.GameBatch(0, seed=1, ctx=ctx)
+    assert L.b2048_games_init(C.byref(empty.c), 0, 1, st) == 0
+    assert L.b2048_greedy_play(2, engine.dptr(w), lut, C.byref(empty.c), 8, 0, 100, None, None, None, None, 0, st) == 0
+    assert L.b2048_expectimax_play(2, engine.dptr(w), lut, C.byref(empty.c), 8, 0, 100, 2, 2, 6, None, None, 0, st) == 0
+    dummy = ctx.zeros(1, torch.int64)
+    assert L.b2048_td_run(2, engine.dptr(w), None, lut, C.byref(empty.c), C.c_float(0.25), 2, 5, engine.dptr(dummy),
+                          engine.dptr(dummy), None, 0, st) == 0
+    games = engine.GameBatch(4, seed=1, ctx=ctx).init()
+    before = games.to_host()
+    tr = engine.TDTrainer(ctx, 2, w, games, 0.25, cabi.UPD_DETERMINISTIC | cabi.UPD_MEAN)
+    tr.run(0)
+    engine.greedy_play(ctx, 2, w, engine.GameBatch(4, seed=1, ctx=ctx).init(), chunk=0, max_launches=1)
+    torch.cuda.synchronize()
+    after = games.to_host()
+    assert np.array_equal(before["board"], after["board"]) and not w.any().item()
+    assert games.read_counters()["moves"] == 0
