@@ -428,6 +428,7 @@ peer_sync_kernel(b2048_peers_t P, int64_t count, uint32_t epoch)
     }
     __syncthreads();
     if (!s_last) return;
+    __threadfence_system();                            // acquire side of the ticket chain: every CTA's fenced stores are ordered before the signal below
     if (threadIdx.x == 0) mine[B2048_PEER_TICKET] = 0;
     if (threadIdx.x < W) {
         if (s_ok) {
