@@ -172,6 +172,7 @@ __device__ __forceinline__ void peer_reduce_slice(const b2048_peers_t &P, int64_
                 if (q == rank) base[k] = bv[k];
             }
         }
+        if (__all_sync(__activemask(), (c[0] | c[1] | c[2] | c[3]) == 0)) continue;   // nobody moved the warp's 128 weights
         float r[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) r[k] = __fadd_rn(base[k], c[k] > 1u ? __fdiv_rn(sum[k], float(c[k])) : sum[k]);
@@ -192,6 +193,7 @@ __device__ __forceinline__ void peer_reduce_slice(const b2048_peers_t &P, int64_
                 c += av != bv;
                 if (q == rank) base = bv;
             }
+            if (c == 0) continue;
             const float out = __fadd_rn(base, c > 1u ? __fdiv_rn(sum, float(c)) : sum);
             for (int q = 0; q < W; q++) { P.w[q][i] = out; P.w_sync[q][i] = out; }
         }
@@ -214,6 +216,7 @@ __device__ __forceinline__ void peer_reduce_slice_scalar(const b2048_peers_t &P,
             c += av != bv;
             if (q == rank) base = bv;
         }
+        if (__all_sync(__activemask(), c == 0)) continue;                  // nobody moved the warp's 32 weights
         const float out = __fadd_rn(base, c > 1u ? __fdiv_rn(sum, float(c)) : sum);
         for (int q = 0; q < W; q++) { P.w[q][i] = out; P.w_sync[q][i] = out; }
     }

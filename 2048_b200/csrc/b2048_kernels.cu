@@ -396,6 +396,10 @@ peer_sync_kernel(b2048_peers_t P, int64_t count, uint32_t epoch)
             float r[4];
 #pragma unroll
             for (int k = 0; k < 4; k++) r[k] = __fadd_rn(base[k], c[k] > 1u ? __fdiv_rn(sum[k], float(c[k])) : sum[k]);
+            // skip the stores where nobody moved any of the 128 weights the warp covers (every replica already holds
+            // w = w_sync = the result there: whole key ranges of large exponents are never touched); decided per warp so
+            // that the remote stores stay full 512-byte runs
+            if (__all_sync(__activemask(), (c[0] | c[1] | c[2] | c[3]) == 0)) continue;
             const float4 out = make_float4(r[0], r[1], r[2], r[3]);
 #pragma unroll
             for (int q = 0; q < W; q++) {
@@ -414,6 +418,7 @@ peer_sync_kernel(b2048_peers_t P, int64_t count, uint32_t epoch)
                     c += av != bv;
                     if (q == rank) base = bv;
                 }
+                if (c == 0) continue;
                 const float out = __fadd_rn(base, c > 1u ? __fdiv_rn(sum, float(c)) : sum);
                 for (int q = 0; q < W; q++) { P.w[q][i] = out; P.w_sync[q][i] = out; }
             }
